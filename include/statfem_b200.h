@@ -1,0 +1,135 @@
+/*
+ * statfem_b200.h -- C ABI of libstatfem_b200.so: the B200 (sm_100a) implementation of stat-fem's data-conditioning
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * The reference (alan-turing-institute/stat-fem) is pure Python with no FFI layer; each entry point below names the
+ * reference statement(s) whose arithmetic it replaces (paths relative to stat_fem/).  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add inside the reference's classes.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless its name ends in _host.  The library never frees
+ *     caller memory; it keeps the pointers passed to sfem_set_stiffness / sfem_set_gcov / sfem_gcov_count until they
+ *     are replaced or the context is destroyed.
+ *   - Dense matrices are row-major.  Multi-RHS blocks are row-major [n x k] with leading dimension ld (k contiguous).
+ *   - CSR: int64 row pointers, int32 column indices (PETSc.IntType, ForcingCovariance.py:164), double values.
+ *   - Every function returns 0 on success or a negative SFEM_ERR_* code; sfem_last_error() gives the message.
+ *   - One context = one GPU = one stream; a context is not thread-safe, distinct contexts are independent.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef STATFEM_B200_H
+#define STATFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfem_ctx sfem_ctx;
+
+#define SFEM_OK 0
+#define SFEM_ERR_CUDA (-1)
+#define SFEM_ERR_ARG (-2)
+#define SFEM_ERR_NOT_SPD (-3)        /* -> scipy.linalg.LinAlgError, as LinearSolver.py:272-276, 602-606 */
+#define SFEM_ERR_NOT_CONVERGED (-4)  /* CG hit max_it */
+#define SFEM_ERR_STATE (-5)
+#define SFEM_ERR_LIMIT (-6)
+
+#define SFEM_OP_N 0
+#define SFEM_OP_T 1
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------- */
+int sfem_version(void);
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for the default stream */
+int sfem_create(sfem_ctx** out, int device, void* cuda_stream);
+int sfem_destroy(sfem_ctx* ctx);
+const char* sfem_last_error(sfem_ctx* ctx);
+long long sfem_launch_count(sfem_ctx* ctx);   /* kernels launched so far by this context */
+
+/* ---- stiffness matrix and the sparse solve (replaces firedrake LinearSolver/PETSc KSP: LinearSolver.py:136-140,
+ *      solving_utils.py:49-53, LinearSolver.py:217) --------------------------------------------------------------- */
+/* A: n x n CSR, symmetric positive definite, Dirichlet rows AND columns replaced by identity (as Firedrake assembles
+ * with bcs=; tests/helper_funcs.py:104-128). */
+int sfem_set_stiffness(sfem_ctx* ctx, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals);
+/* Build the lattice multigrid preconditioner.  coords: n x dim row-major DOF coordinates; bc_mask: n bytes (1 =
+ * Dirichlet DOF); lo/hi_host: bounding box; m1_host: level-1 lattice nodes per direction (2^p + 1 each);
+ * nu: Jacobi sweeps before and after; omega: damping; max_coarse: coarsen until a level has at most this many nodes. */
+int sfem_mg_setup(sfem_ctx* ctx, int dim, const double* coords, const uint8_t* bc_mask, const double* lo_host,
+                  const double* hi_host, const int* m1_host, int nu, double omega, int max_coarse);
+int sfem_mg_num_levels(sfem_ctx* ctx);
+int64_t sfem_mg_level_size(sfem_ctx* ctx, int level);
+size_t sfem_solve_workspace_bytes(sfem_ctx* ctx, int k, int precond);
+/* X (n x k, ldx) = A^-1 B (n x k, ldb): k independent PCG recurrences advanced in lock-step.  precond: 0 Jacobi,
+ * 1 multigrid V-cycle.  Stops when ||r||_2 <= max(rtol ||b||_2, atol) for every column.  iters_out_host: iterations;
+ * relres_out_host[k]: TRUE relative residuals ||b - A x|| / ||b|| recomputed at the end. */
+int sfem_solve_block(sfem_ctx* ctx, int k, const double* B, int64_t ldb, double* X, int64_t ldx, int precond,
+                     double rtol, double atol, int max_it, int* iters_out_host, double* relres_out_host, void* work,
+                     size_t work_bytes);
+
+/* ---- generic CSR SpMM on multi-RHS blocks: Y (nrows x k) = S X.  Used for P d (InterpolationMatrix.py:213-221), P^T v
+ *      (InterpolationMatrix.py:254-259, with P's CSC arrays read as the CSR of P^T) and G x (ForcingCovariance.py:242). */
+int sfem_spmm_csr(sfem_ctx* ctx, int64_t nrows, const int64_t* indptr, const int32_t* indices, const double* vals, int k,
+                  const double* X, int64_t ldx, double* Y, int64_t ldy);
+/* B (n x k, ldb) = dense copy of columns [col_begin, col_begin+k) of the CSC matrix P
+ * (InterpolationMatrix.get_meshspace_column_vector, InterpolationMatrix.py:261-287, for a whole block of sensors). */
+int sfem_scatter_columns(sfem_ctx* ctx, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,
+                         int64_t col_begin, int k, double* B, int64_t ldb);
+
+/* ---- forcing covariance assembly (replaces ForcingCovariance._compute_G_vals + assemble, ForcingCovariance.py:130-197) */
+/* Pass 1: cell list + per-row count.  exp_2sigma = exp(2 sigma), exp_m2l = exp(-2 l) evaluated by the caller (so they
+ * match the reference's NumPy values bitwise).  bmax = max(int_basis).  cell_edge >= the largest distance at which
+ * row[j]/row[i] > cutoff can hold (0: all pairs, required when cutoff <= 0).  indptr_out: n+1 int64 (device).
+ * borderline_rows (device, capacity borderline_cap): rows holding a ratio within 1e-14 (relative) of the cutoff. */
+int sfem_gcov_count(sfem_ctx* ctx, int64_t n, int dim, const double* coords, const double* int_basis, double exp_2sigma,
+                    double exp_m2l, double cutoff, double regularization, double bmax, double cell_edge,
+                    const double* lo_host, const double* hi_host, int64_t* indptr_out, int64_t* nnz_out_host,
+                    int64_t* max_row_nnz_out_host, int32_t* borderline_rows, int borderline_cap,
+                    int64_t* n_borderline_out_host);
+/* Pass 2: write ascending int32 columns and values for the pattern counted by pass 1. */
+int sfem_gcov_fill(sfem_ctx* ctx, const int64_t* indptr, int32_t* indices_out, double* vals_out);
+
+/* ---- dense FP64 tensor-core primitives (replace NumPy/SciPy BLAS+LAPACK calls of LinearSolver.py) ---------------- */
+/* C (M x N, ldc) = alpha op(A) op(B) + beta C.  opA = SFEM_OP_T means A is stored K x M.  Cu = W^T Z is
+ * sfem_dgemm(T, N, n_obs, n_cols, n_dof, 1, W, ldw, Z, ldz, 0, Cu, ldcu)  (solving_utils.py:139-142, 164-169). */
+int sfem_dgemm(sfem_ctx* ctx, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
+               const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+size_t sfem_potrf_dinv_doubles(int n);
+/* In-place lower Cholesky of the row-major n x n matrix A (only the lower triangle is read); dinv receives the
+ * inverses of the 128x128 diagonal blocks.  info_out_host: 0 or the 1-based index of the first non-positive pivot. */
+int sfem_potrf(sfem_ctx* ctx, int n, double* A, int64_t lda, double* dinv, int* info_out_host);
+int sfem_potrs(sfem_ctx* ctx, int n, const double* L, int64_t ldl, const double* dinv, int k, double* B, int64_t ldb);
+int sfem_potri(sfem_ctx* ctx, int n, const double* L, int64_t ldl, const double* dinv, double* work_nn, double* Kinv);
+int sfem_logdet(sfem_ctx* ctx, int n, const double* L, int64_t ldl, double* out_host);
+
+/* ---- model-discrepancy matrices and the fused dense end (ObsData.py:131-214; LinearSolver.py:351-367, 600-613, 659-681) */
+/* which = 0: M = sqexp(Xs,Xs,sigma,l) [+ diag(unc^2) if unc != NULL] [+ rho2 * sym_upper(Cu) if Cu != NULL]
+ * which = 1: dK/dsigma = 2K;  which = 2: dK/dl.   Xs: n_obs x dim.  unc: 1 value, or n_obs values if unc_is_vector. */
+int sfem_kernel_matrix(sfem_ctx* ctx, int n_obs, int dim, const double* Xs, double sigma, double l, const double* unc,
+                       int unc_is_vector, double rho2, const double* Cu, int which, double* M_out);
+/* Rectangular covariance block between two point sets X1 (m x dim) and X2 (n x dim) -> M_out (m x n):
+ * which = 0 sqexp, 1 d/dsigma, 2 d/dl, 3 squared distance (covariance_functions.py:4-37, 39-77, 122-145). */
+int sfem_cov_matrix(sfem_ctx* ctx, int m, int n, int dim, const double* X1, const double* X2, double sigma, double l,
+                    int which, double* M_out);
+/* z = a x + b y on device vectors (y may be NULL): the mesh-space combinations of LinearSolver.py:287, 303-305. */
+int sfem_axpby(sfem_ctx* ctx, int64_t n, double a, const double* x, double b, const double* y, double* z);
+size_t sfem_dense_workspace_bytes(int n_obs);
+/* Negative log marginal likelihood and (if grad_out_host != NULL) its gradient at theta_host = (log rho, log sigma_eta,
+ * log l_eta): LinearSolver.logposterior / logpost_deriv. */
+int sfem_logpost(sfem_ctx* ctx, int n_obs, int dim, const double* Xs, const double* y, const double* unc,
+                 int unc_is_vector, const double* mu, const double* Cu, const double* theta_host, double* value_out_host,
+                 double* grad_out_host, void* work, size_t work_bytes);
+/* LinearSolver.solve_posterior_covariance: muy_out (n_obs), Cuy_out (n_obs x n_obs), unscaled. */
+int sfem_posterior_cov(sfem_ctx* ctx, int n_obs, int dim, const double* Xs, const double* y, const double* unc,
+                       int unc_is_vector, const double* mu, const double* Cu, const double* theta_host, double* muy_out,
+                       double* Cuy_out, void* work, size_t work_bytes);
+/* x = (K + diag(unc^2) + rho2 sym_upper(Cu))^-1 b : the data-space solves of LinearSolver.solve_posterior
+ * (LinearSolver.py:271-277, 291-297).  Cu may be NULL when rho2 == 0. */
+int sfem_dense_solve(sfem_ctx* ctx, int n_obs, int dim, const double* Xs, const double* unc, int unc_is_vector,
+                     double sigma, double l, double rho2, const double* Cu, const double* b, double* x, void* work,
+                     size_t work_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STATFEM_B200_H */

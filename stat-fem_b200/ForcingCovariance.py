@@ -1,0 +1,168 @@
+"""Sparse forcing covariance G (API of ForcingCovariance.py in the reference), assembled on the GPU.
+
+The reference computes every one of the n^2 candidate entries in a Python loop and keeps those whose value relative
+to the (nugget-regularised) diagonal exceeds ``cutoff`` (ForcingCovariance.py:159-167).  Here the same rule is applied
+by the cell-list kernels of csrc/gcov.cu; the resulting CSR pattern (int32 ascending columns) is bit-identical and
+the values agree to the last ulp or two of ``exp``."""
+import ctypes as C
+import numpy as np
+from . import _lib
+from . import fem
+from .covariance_functions import sqexp
+
+_BORDER_CAP = 4096
+
+
+class ForcingCovariance(object):
+    def __init__(self, function_space, sigma, l, cutoff=1.e-3, regularization=1.e-8, cov=sqexp):
+        if not isinstance(function_space, fem.P1Space):
+            raise TypeError("bad input type for function_space: must be a FunctionSpace")
+        self.function_space = function_space
+        self.comm = function_space.comm
+        self.nx = function_space.dim()
+        self.nx_local = function_space.dim()
+        assert regularization >= 0., "regularization parameter must be non-negative"
+        self.sigma = sigma
+        self.l = l
+        self.cutoff = cutoff
+        self.regularization = regularization
+        self.cov = cov
+        self.local_startind, self.local_endind = 0, self.nx
+        self.is_assembled = False
+        self.G = None
+        self.max_row_nnz = 0
+        self.n_borderline = 0
+
+    def _integrate_basis_functions(self):
+        "int phi_i dx for every DOF (ForcingCovariance.py:111-128)"
+        return np.array(self.function_space.integrate_basis_functions())
+
+    # ---- host-side scalars for the kernel -----------------------------------------------------------------
+    def _search_radius(self, int_basis):
+        """largest distance at which row[j]/row[i] > cutoff can hold for any row (0 -> all pairs)"""
+        if self.cutoff <= 0.:
+            return 0.
+        b = int_basis
+        e2s = np.exp(2. * self.sigma)
+        arg = b * b.max() * e2s / (self.cutoff * (b * b * e2s + self.regularization))
+        amax = float(arg.max())
+        if amax <= 1.:
+            return -1.      # nothing but the diagonal can pass
+        return float(np.sqrt(2. * np.exp(2. * self.l) * np.log(amax)) * (1. + 1.e-5))
+
+    def _host_rows(self, rows, coords, int_basis):
+        """Re-evaluate complete rows with the reference's NumPy/SciPy expression (ForcingCovariance.py:159-164).  Only
+        used for the handful of rows the kernel flags as containing a ratio within 1e-14 of the cutoff."""
+        from scipy.spatial.distance import cdist
+        out = {}
+        e2s, em2l = np.exp(2. * self.sigma), np.exp(-2. * self.l)
+        for i in rows:
+            r2 = cdist(np.atleast_2d(coords[i]), coords) ** 2
+            row = (int_basis[i] * int_basis * (e2s * np.exp(-0.5 * r2 * em2l)))[0]
+            row[i] += self.regularization
+            keep = (row / row[i] > self.cutoff)
+            out[int(i)] = (row[keep], np.nonzero(keep)[0].astype(np.int32))
+        return out
+
+    def assemble(self):
+        "compute G on the GPU (idempotent, ForcingCovariance.py:171-197)"
+        if self.is_assembled:
+            return
+        if self.cov is not sqexp:
+            raise NotImplementedError("only the squared-exponential covariance is implemented on the GPU; "
+                                      "there is no CPU path for user-supplied covariance callables")
+        ctx = _lib.get_context()
+        lib = _lib.lib()
+        coords = np.ascontiguousarray(self.function_space.coords, dtype=np.float64)
+        n, d = coords.shape
+        int_basis = self._integrate_basis_functions()
+        R = self._search_radius(int_basis)
+        lo, hi = coords.min(axis=0), coords.max(axis=0)
+        if R < 0.:
+            cell_edge = float(max((hi - lo).max(), 1.) * 1.e-3)      # diagonal only: any small cell will do
+            cell_edge = max(cell_edge, float((hi - lo).max()) / 2048.)
+        else:
+            cell_edge = R
+            if R > 0. and float((hi - lo).max()) / R >= 4000.:
+                raise ValueError("cutoff radius is too small relative to the domain for the cell list")
+        d_coords = ctx.to_device(coords, np.float64)
+        d_b = ctx.to_device(int_basis, np.float64)
+        import torch
+        d_indptr = ctx.empty((n + 1,), torch.int64)
+        d_border = ctx.empty((_BORDER_CAP,), torch.int32)
+        nnz, maxnnz, nborder = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        lo3 = (C.c_double * 3)(*(list(lo) + [0.] * (3 - d)))
+        hi3 = (C.c_double * 3)(*(list(hi) + [0.] * (3 - d)))
+        ctx.check(lib.sfem_gcov_count(ctx.handle, n, d, _lib.ptr(d_coords), _lib.ptr(d_b),
+                                      float(np.exp(2. * self.sigma)), float(np.exp(-2. * self.l)), float(self.cutoff),
+                                      float(self.regularization), float(int_basis.max()), float(cell_edge), lo3, hi3,
+                                      _lib.ptr(d_indptr), C.byref(nnz), C.byref(maxnnz), _lib.ptr(d_border),
+                                      _BORDER_CAP, C.byref(nborder)))
+        d_indices = ctx.empty((max(nnz.value, 1),), torch.int32)
+        d_vals = ctx.empty((max(nnz.value, 1),), torch.float64)
+        ctx.check(lib.sfem_gcov_fill(ctx.handle, _lib.ptr(d_indptr), _lib.ptr(d_indices), _lib.ptr(d_vals)))
+        d_indices, d_vals = d_indices[:nnz.value], d_vals[:nnz.value]
+        self.max_row_nnz = int(maxnnz.value)
+        self.n_borderline = int(nborder.value)
+        if self.n_borderline > 0:
+            d_indptr, d_indices, d_vals = self._redecide(ctx, d_indptr, d_indices, d_vals, d_border, coords, int_basis)
+        self.G = _lib.DeviceCSR(ctx, (n, n), d_indptr, d_indices, d_vals, on_device=True)
+        self.is_assembled = True
+
+    def _redecide(self, ctx, d_indptr, d_indices, d_vals, d_border, coords, int_basis):
+        """Splice host-decided rows into the CSR arrays (rare: a ratio landed within 1e-14 of the cutoff)."""
+        n = self.nx
+        if self.n_borderline > _BORDER_CAP:
+            rows = np.arange(n)
+        else:
+            rows = np.unique(d_border[:self.n_borderline].cpu().numpy())
+        fixed = self._host_rows(rows, coords, int_basis)
+        indptr, indices, vals = d_indptr.cpu().numpy(), d_indices.cpu().numpy(), d_vals.cpu().numpy()
+        counts = np.diff(indptr)
+        for i, (v, cidx) in fixed.items():
+            counts[i] = len(cidx)
+        new_ptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(counts, out=new_ptr[1:])
+        new_idx = np.empty(new_ptr[-1], dtype=np.int32)
+        new_val = np.empty(new_ptr[-1], dtype=np.float64)
+        for i in range(n):
+            if i in fixed:
+                new_val[new_ptr[i]:new_ptr[i + 1]], new_idx[new_ptr[i]:new_ptr[i + 1]] = fixed[i]
+            else:
+                new_idx[new_ptr[i]:new_ptr[i + 1]] = indices[indptr[i]:indptr[i + 1]]
+                new_val[new_ptr[i]:new_ptr[i + 1]] = vals[indptr[i]:indptr[i + 1]]
+        self.max_row_nnz = int(counts.max())
+        return ctx.to_device(new_ptr, np.int64), ctx.to_device(new_idx, np.int32), ctx.to_device(new_val, np.float64)
+
+    def _compute_G_vals(self):
+        """(dict row -> (values, int32 columns), max_row_nnz) like ForcingCovariance.py:130-169, read back from the
+        GPU-assembled matrix."""
+        self.assemble()
+        indptr, indices, vals = self.G.to_host()
+        G_dict = {i: (vals[indptr[i]:indptr[i + 1]], indices[indptr[i]:indptr[i + 1]]) for i in range(self.nx)}
+        return G_dict, self.max_row_nnz
+
+    def destroy(self):
+        if not self.is_assembled:
+            return
+        self.G = None
+        self.is_assembled = False
+
+    def mult(self, x, y):
+        "y <- G x for mesh-space vectors (ForcingCovariance.py:212-242)"
+        assert isinstance(x, fem.Vector), "x must be a firedrake vector"
+        assert isinstance(y, fem.Vector), "y must be a firedrake vector"
+        if not self.is_assembled:
+            self.assemble()
+        ctx = self.G.ctx
+        dx = ctx.to_device(x.array, np.float64)
+        y.set_local(self.G.matmul(dx).cpu().numpy())
+
+    def get_nx(self):
+        return self.nx
+
+    def get_nx_local(self):
+        return self.nx_local
+
+    def __str__(self):
+        return "Forcing Covariance with {} mesh points".format(self.get_nx())

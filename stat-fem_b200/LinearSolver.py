@@ -1,0 +1,340 @@
+"""LinearSolver: all stat-fem solves for one FEM model + one data set (API of LinearSolver.py in the reference).
+
+Caches the prior solution x, its interpolation mu and the interpolated prior covariance Cu (LinearSolver.py:150-153,
+210-222) -- here on the device as well as on the host -- and evaluates every dense n_obs x n_obs quantity with the
+FP64 tensor-core kernels (csrc/dgemm.cu, chol.cu, dense_ops.cu)."""
+import ctypes as C
+import numpy as np
+from scipy.linalg import LinAlgError
+from . import _lib
+from . import fem
+from .parallel import EnsembleComm, COMM_SELF, comm_world
+from .ForcingCovariance import ForcingCovariance
+from .InterpolationMatrix import InterpolationMatrix
+from .ObsData import ObsData
+from .solving_utils import SparseSolver, interp_covariance_to_data, _aga_device
+
+
+class LinearSolver(object):
+    def __init__(self, A, b, G, data, *, priors=[None, None, None], ensemble_comm=COMM_SELF, P=None,
+                 solver_parameters=None, nullspace=None, transpose_nullspace=None, near_nullspace=None,
+                 options_prefix=None):
+        if not isinstance(A, fem.Matrix):
+            raise TypeError("A must be a firedrake matrix")
+        if not isinstance(b, (fem.Function, fem.Vector)):
+            raise TypeError("b must be a firedrake function or vector")
+        if not isinstance(G, ForcingCovariance):
+            raise TypeError("G must be a forcing covariance")
+        if not isinstance(data, ObsData):
+            raise TypeError("data must be an ObsData type")
+        if not isinstance(priors, list):
+            raise TypeError("priors must be a list of prior objects or None")
+        if not len(priors) == 3:
+            raise ValueError("priors must be a list of prior objects or None of length 3")
+        for p in priors:
+            if p is not None:
+                raise TypeError("priors must be a list of prior objects or None")
+        if not isinstance(ensemble_comm, EnsembleComm):
+            raise TypeError("ensemble_comm must be an MPI communicator created with a firedrake Ensemble")
+        self.solver = SparseSolver(A, P=P, solver_parameters=solver_parameters, nullspace=nullspace,
+                                   transpose_nullspace=transpose_nullspace, near_nullspace=near_nullspace,
+                                   options_prefix=options_prefix)
+        self.b = b
+        self.G = G
+        self.data = data
+        self.ensemble_comm = ensemble_comm
+        self.priors = list(priors)
+        self.params = None
+        self.im = InterpolationMatrix(G.function_space, data.get_coords())
+        self.x = None
+        self.mu = None
+        self.Cu = None
+        self.current_logpost = None
+        # device mirrors + evaluation cache
+        self._x_dev = self._mu_dev = self._Cu_dev = None
+        self._dense_work = None
+        self._cache = None
+        self.fuse_gradient = False      # set by estimate_params_MAP: evaluate value and gradient in one pass
+        self.n_logpost_evals = 0
+
+    def __del__(self):
+        try:
+            self.im.destroy()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        "hyperparameters (log rho, log sigma_eta, log l_eta) (LinearSolver.py:165-183)"
+        params = np.array(params, dtype=np.float64)
+        assert params.shape == (3,), "bad shape for model discrepancy parameters"
+        self.params = params
+
+    # ---------------------------------------------------------------------------------------------------------
+    @property
+    def _root(self):
+        return self.ensemble_comm.rank == 0 and self.G.comm.rank == 0
+
+    def _work(self):
+        n = self.data.get_n_obs()
+        need = _lib.lib().sfem_dense_workspace_bytes(n)
+        if self._dense_work is None or self._dense_work.numel() < need + 256:
+            self._dense_work = self.solver.ctx.workspace(need)
+        w = self._dense_work
+        off = (-w.data_ptr()) % 256
+        return C.c_void_p(w.data_ptr() + off), int(w.numel() - off)
+
+    def solve_prior(self):
+        "prior mean and covariance at the sensors (LinearSolver.py:185-222)"
+        ctx = self.solver.ctx
+        Cu_dev = interp_covariance_to_data(self.im, self.G, self.solver, self.im, self.ensemble_comm, return_device=True)
+        self.x = fem.Function(self.G.function_space)
+        if self.ensemble_comm.rank == 0:
+            bf = self.b.function if isinstance(self.b, fem.Vector) else self.b
+            self._x_dev = self.solver.solve_vector(ctx.to_device(bf.data, np.float64),
+                                                   apply_bcs=self.solver.A.bcs is not None)
+            self.x.data[:] = self._x_dev.cpu().numpy()
+            self._mu_dev = self.im.csc.matmul(self._x_dev)
+            self.mu = self._mu_dev.cpu().numpy()
+        else:
+            self.mu = np.zeros(0)
+        if Cu_dev is not None:
+            self._Cu_dev = Cu_dev.contiguous()
+            self.Cu = self._Cu_dev.cpu().numpy()
+        else:
+            self.Cu = np.zeros((0, 0))
+        self._cache = None
+        return self.mu, self.Cu
+
+    def _dense_solve(self, rho2, with_Cu, b_dev):
+        d = self.data.device()
+        ctx = self.solver.ctx
+        out = ctx.empty((self.data.get_n_obs(),))
+        work, nbytes = self._work()
+        ctx.check(_lib.lib().sfem_dense_solve(ctx.handle, self.data.get_n_obs(), self.data.get_n_dim(), _lib.ptr(d["coords"]),
+                                              _lib.ptr(d["unc"]), d["unc_vec"], float(self.params[1]), float(self.params[2]),
+                                              float(rho2), _lib.ptr(self._Cu_dev if with_Cu else None), _lib.ptr(b_dev),
+                                              _lib.ptr(out), work, nbytes))
+        return out
+
+    def _axpby(self, a, x, b, y):
+        ctx = self.solver.ctx
+        z = ctx.empty((x.shape[0],))
+        ctx.check(_lib.lib().sfem_axpby(ctx.handle, x.shape[0], float(a), _lib.ptr(x), float(b), _lib.ptr(y), _lib.ptr(z)))
+        return z
+
+    def solve_posterior(self, x, scale_mean=False):
+        "posterior mean on the mesh, written into ``x`` on the ensemble root (LinearSolver.py:224-305)"
+        if not isinstance(bool(scale_mean), bool):
+            raise TypeError("scale_mean argument must be boolean-like")
+        if self.Cu is None or self.x is None:
+            self.solve_prior()
+        if self.params is None:
+            raise ValueError("must set parameter values to solve posterior")
+        rho = np.exp(self.params[0])
+        scalefact = rho if scale_mean else 1.
+        if self.ensemble_comm.rank == 0:
+            d = self.data.device()
+            try:
+                t1 = self._dense_solve(0., False, d["data"])
+            except LinAlgError:
+                raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy")
+            m1 = self.im.csr.matmul(t1)
+            m2 = self._axpby(rho, _aga_device(self.G, self.solver, m1), 1., self._x_dev)
+            d1 = self.im.csc.matmul(m2)
+            try:
+                d2 = self._dense_solve(rho ** 2, True, d1)
+            except LinAlgError:
+                raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy "
+                                  "plus forcing covariance")
+            m3 = _aga_device(self.G, self.solver, self.im.csr.matmul(d2))
+            out = self._axpby(scalefact, m2, -scalefact * rho ** 2, m3)
+            xf = x.function if isinstance(x, fem.Vector) else x
+            xf.data[:] = out.cpu().numpy()
+
+    def solve_posterior_covariance(self, scale_mean=False):
+        "posterior mean and covariance at the sensors (LinearSolver.py:308-373)"
+        if not isinstance(bool(scale_mean), bool):
+            raise TypeError("scale_mean argument must be boolean-like")
+        if self.mu is None or self.Cu is None:
+            self.solve_prior()
+        if self.params is None:
+            raise ValueError("must set parameter values to solve posterior")
+        rho = np.exp(self.params[0])
+        scalefact = rho if scale_mean else 1.
+        if self._root:
+            n = self.data.get_n_obs()
+            d = self.data.device()
+            ctx = self.solver.ctx
+            muy, Cuy = ctx.empty((n,)), ctx.empty((n, n))
+            theta = (C.c_double * 3)(*self.params)
+            work, nbytes = self._work()
+            try:
+                ctx.check(_lib.lib().sfem_posterior_cov(ctx.handle, n, self.data.get_n_dim(), _lib.ptr(d["coords"]),
+                                                        _lib.ptr(d["data"]), _lib.ptr(d["unc"]), d["unc_vec"],
+                                                        _lib.ptr(self._mu_dev), _lib.ptr(self._Cu_dev), theta,
+                                                        _lib.ptr(muy), _lib.ptr(Cuy), work, nbytes))
+            except LinAlgError:
+                raise LinAlgError("Cholesky factorization of one of the covariance matrices failed")
+            return scalefact * muy.cpu().numpy(), Cuy.cpu().numpy()
+        return scalefact * np.zeros(0), np.zeros((0, 0))
+
+    def solve_prior_generating(self):
+        "prior of the generating process rho u + eta at the sensors (LinearSolver.py:375-406)"
+        if self.mu is None or self.Cu is None:
+            self.solve_prior()
+        if self.params is None:
+            raise ValueError("must set parameter values to solve prior of generating process")
+        rho = np.exp(self.params[0])
+        if self._root:
+            return rho * self.mu, self._kcu_matrix(rho ** 2, with_unc=False)
+        return np.zeros(0), np.zeros((0, 0))
+
+    def _kcu_matrix(self, rho2, with_unc, symmetric_upper=False):
+        """K_eta [+ diag(unc^2)] + rho2 * Cu on the device -> host.  The generating-process prior adds the full
+        (slightly non-symmetric) Cu, as NumPy does at LinearSolver.py:401."""
+        d = self.data.device()
+        ctx = self.solver.ctx
+        n = self.data.get_n_obs()
+        K = ctx.empty((n, n))
+        ctx.check(_lib.lib().sfem_kernel_matrix(ctx.handle, n, self.data.get_n_dim(), _lib.ptr(d["coords"]),
+                                                float(self.params[1]), float(self.params[2]),
+                                                _lib.ptr(d["unc"] if with_unc else None), d["unc_vec"], 0., _lib.ptr(None), 0,
+                                                _lib.ptr(K)))
+        return rho2 * self.Cu + K.cpu().numpy()
+
+    def solve_posterior_generating(self):
+        "posterior of the generating process at the sensors (LinearSolver.py:408-439)"
+        m_eta, C_eta = self.solve_prior_generating()
+        if self._root:
+            n = self.data.get_n_obs()
+            ctx = self.solver.ctx
+            lib = _lib.lib()
+            unc2 = self.data.get_unc() ** 2
+            # SciPy's default cho_factor reads the upper triangle: mirror it so the lower factorisation sees the same matrix
+            Mh = unc2 * np.eye(n) + C_eta
+            M = ctx.to_device(np.triu(Mh) + np.triu(Mh, 1).T, np.float64)
+            dinv = ctx.empty((lib.sfem_potrf_dinv_doubles(n),))
+            info = C.c_int(0)
+            try:
+                ctx.check(lib.sfem_potrf(ctx.handle, n, _lib.ptr(M), n, _lib.ptr(dinv), C.byref(info)))
+            except LinAlgError:
+                raise LinAlgError("Cholesky factorization of the covariance matrix failed")
+            rhs = np.concatenate([unc2 * C_eta, (np.dot(C_eta, self.data.get_data()) + unc2 * m_eta)[:, None]], axis=1)
+            B = ctx.to_device(rhs, np.float64)
+            ctx.check(lib.sfem_potrs(ctx.handle, n, _lib.ptr(M), n, _lib.ptr(dinv), n + 1, _lib.ptr(B), n + 1))
+            sol = B.cpu().numpy()
+            return sol[:, n].copy(), sol[:, :n].copy()
+        return np.zeros(0), np.zeros((0, 0))
+
+    def predict_mean(self, coords, scale_mean=True):
+        "posterior mean at new locations (LinearSolver.py:441-498)"
+        if not isinstance(bool(scale_mean), bool):
+            raise TypeError("scale_mean argument must be boolean-like")
+        coords = np.array(coords, dtype=np.float64)
+        if coords.ndim == 1:
+            coords = np.reshape(coords, (-1, 1))
+        assert coords.ndim == 2, "coords must be a 1d or 2d array"
+        assert coords.shape[1] == self.data.get_n_dim(), "axis 1 of coords must be the same length as the FEM dimension"
+        if self.Cu is None:
+            self.solve_prior()
+        if self.params is None:
+            raise ValueError("must set parameter values to make predictions")
+        scalefact = np.exp(self.params[0]) if scale_mean else 1.
+        x = fem.Function(self.G.function_space)
+        self.solve_posterior(x)
+        im = InterpolationMatrix(self.G.function_space, coords)
+        mu = scalefact * im.interp_mesh_to_data(x.vector())
+        im.destroy()
+        return mu
+
+    def predict_covariance(self, coords, unc):
+        "predictive covariance at new locations (LinearSolver.py:500-567)"
+        coords = np.array(coords, dtype=np.float64)
+        if coords.ndim == 1:
+            coords = np.reshape(coords, (-1, 1))
+        assert coords.ndim == 2, "coords must be a 1d or 2d array"
+        assert coords.shape[1] == self.data.get_n_dim(), "axis 1 of coords must be the same length as the FEM dimension"
+        if self.Cu is None:
+            self.solve_prior()
+        if self.params is None:
+            raise ValueError("must set parameter values to make predictions")
+        rho = np.exp(self.params[0])
+        im_coords = InterpolationMatrix(self.G.function_space, coords)
+        if coords.shape[0] > self.data.get_n_obs():
+            Cucd = interp_covariance_to_data(im_coords, self.G, self.solver, self.im, self.ensemble_comm)
+        else:
+            Cucd = interp_covariance_to_data(self.im, self.G, self.solver, im_coords, self.ensemble_comm).T
+        Cucc = interp_covariance_to_data(im_coords, self.G, self.solver, im_coords, self.ensemble_comm)
+        if self._root:
+            n = self.data.get_n_obs()
+            d = self.data.device()
+            ctx = self.solver.ctx
+            lib = _lib.lib()
+            M = ctx.empty((n, n))
+            ctx.check(lib.sfem_kernel_matrix(ctx.handle, n, self.data.get_n_dim(), _lib.ptr(d["coords"]),
+                                             float(self.params[1]), float(self.params[2]), _lib.ptr(d["unc"]), d["unc_vec"],
+                                             float(rho ** 2), _lib.ptr(self._Cu_dev), 0, _lib.ptr(M)))
+            dinv = ctx.empty((lib.sfem_potrf_dinv_doubles(n),))
+            info = C.c_int(0)
+            try:
+                ctx.check(lib.sfem_potrf(ctx.handle, n, _lib.ptr(M), n, _lib.ptr(dinv), C.byref(info)))
+            except LinAlgError:
+                raise LinAlgError("Cholesky factorization of one of the covariance matrices failed")
+            nc = coords.shape[0]
+            B = ctx.to_device(np.ascontiguousarray(Cucd.T), np.float64)          # n x nc
+            ctx.check(lib.sfem_potrs(ctx.handle, n, _lib.ptr(M), n, _lib.ptr(dinv), nc, _lib.ptr(B), nc))
+            Cd = ctx.to_device(Cucd, np.float64)                                   # nc x n
+            Cuy = ctx.to_device(Cucc, np.float64)
+            ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_N, _lib.OP_N, nc, nc, n, -rho ** 2, _lib.ptr(Cd), n, _lib.ptr(B), nc,
+                                     1.0, _lib.ptr(Cuy), nc))
+            Knew = ObsData(coords, np.zeros(coords.shape[0]), unc).calc_K_plus_sigma(self.params[1:])
+            out = Knew + rho ** 2 * Cuy.cpu().numpy()
+        else:
+            out = np.zeros((0, 0))
+        im_coords.destroy()
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _evaluate(self, params, need_grad):
+        "negative log marginal likelihood (and gradient) on the device; identical result on every process"
+        self.set_params(params)
+        if self.Cu is None or self.mu is None:
+            self.solve_prior()
+        key = self.params.tobytes()
+        if self._cache is not None and self._cache[0] == key and (self._cache[2] is not None or not need_grad):
+            return self._cache[1], self._cache[2]
+        world = comm_world()
+        if world.rank == 0:
+            n = self.data.get_n_obs()
+            d = self.data.device()
+            ctx = self.solver.ctx
+            theta = (C.c_double * 3)(*self.params)
+            value = C.c_double(0.)
+            grad = (C.c_double * 3)()
+            work, nbytes = self._work()
+            try:
+                ctx.check(_lib.lib().sfem_logpost(ctx.handle, n, self.data.get_n_dim(), _lib.ptr(d["coords"]),
+                                                  _lib.ptr(d["data"]), _lib.ptr(d["unc"]), d["unc_vec"], _lib.ptr(self._mu_dev),
+                                                  _lib.ptr(self._Cu_dev), theta, C.byref(value),
+                                                  grad if need_grad else None, work, nbytes))
+            except LinAlgError:
+                raise LinAlgError("Error attempting to factorize the covariance matrix in model_loglikelihood")
+            self.n_logpost_evals += 1
+            result = (float(value.value), np.array(list(grad), dtype=np.float64) if need_grad else None)
+        else:
+            result = None
+        result = world.bcast(result, root=0)
+        assert result is not None, "error in broadcasting the log likelihood"
+        world.barrier()
+        self._cache = (key, result[0], result[1])
+        return result
+
+    def logposterior(self, params):
+        "negative log posterior (LinearSolver.py:569-623); priors are always None (LinearSolver.py:130-132)"
+        value, _ = self._evaluate(params, need_grad=self.fuse_gradient)
+        return value
+
+    def logpost_deriv(self, params):
+        "gradient of the negative log posterior wrt the three log-parameters (LinearSolver.py:625-691)"
+        _, grad = self._evaluate(params, need_grad=True)
+        return grad.copy()

@@ -1,0 +1,97 @@
+// Shared declarations for libstatfem_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#define SFEM_OK 0
+#define SFEM_ERR_CUDA (-1)
+#define SFEM_ERR_ARG (-2)
+#define SFEM_ERR_NOT_SPD (-3)
+#define SFEM_ERR_NOT_CONVERGED (-4)
+#define SFEM_ERR_STATE (-5)
+#define SFEM_ERR_LIMIT (-6)
+
+struct MGLevel;   // mg.cu
+
+struct sfem_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[1024] = {0};
+    long long launches = 0;          // kernels launched by this library (bench.py's gpu_launches)
+
+    // ---- stiffness A (caller-owned CSR; identity Dirichlet rows/cols) -------------------------------
+    int64_t n = 0;
+    const int64_t* A_ptr = nullptr;
+    const int32_t* A_idx = nullptr;
+    const double* A_val = nullptr;
+    double* A_dinv = nullptr;        // owned: 1/diag(A)
+    int64_t A_nnz = 0;
+
+    // ---- forcing covariance G (caller-owned CSR) -----------------------------------------------------
+    int64_t g_n = 0;
+    const int64_t* G_ptr = nullptr;
+    const int32_t* G_idx = nullptr;
+    const double* G_val = nullptr;
+
+    // ---- cell list kept between gcov_count and gcov_fill (owned) --------------------------------------
+    struct {
+        int64_t n = 0; int d = 0;
+        const double* coords = nullptr; const double* b = nullptr;
+        double e2s = 0, em2l = 0, cutoff = 0, reg = 0, bmax = 0, two_e2l = 0;
+        double lo[3] = {0, 0, 0}; double inv_edge = 0; int nc[3] = {1, 1, 1}; int ncell = 1;
+        int* cell_start = nullptr;   // ncell+1
+        int* cell_nodes = nullptr;   // n, ascending node index inside each cell
+        int64_t max_row_nnz = 0;
+    } gc;
+
+    // ---- multigrid hierarchy (owned) -------------------------------------------------------------------
+    std::vector<MGLevel*> mg;
+    int mg_nu_pre = 2, mg_nu_post = 2;
+    double mg_omega = 0.8;
+
+    // ---- scratch arena (owned, grows) --------------------------------------------------------------------
+    void* scratch = nullptr; size_t scratch_bytes = 0;
+    void* pinned = nullptr;          // small pinned host buffer for scalar read-backs
+};
+
+int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);
+void* sfem_scratch(sfem_ctx* c, size_t bytes);   // returns device scratch of at least `bytes` (may realloc)
+
+#define CUDA_TRY(c, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return sfem_fail((c), SFEM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,     \
+                             cudaGetErrorString(_e));                                             \
+    } while (0)
+
+#define KCHECK(c)                                                                                 \
+    do {                                                                                          \
+        (c)->launches++;                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess)                                                                    \
+            return sfem_fail((c), SFEM_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, \
+                             cudaGetErrorString(_e));                                             \
+    } while (0)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+#define SFEM_NUM_SMS 148
+
+// ---- internal entry points shared between translation units -------------------------------------------------
+// spmm.cu
+int spmm_csr(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val,
+             int k, const double* X, int64_t ldx, double* Y, int64_t ldy,
+             double* dot_partials /*nullable: [nblk][k] of sum_i X[i][c]*Y[i][c]*/, int* nblk_out);
+// dgemm.cu
+enum { OP_N = 0, OP_T = 1 };
+int dgemm(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only);
+// mg.cu
+int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_t ldz, double* tmp0, void* work);
+void mg_free(sfem_ctx* c);

@@ -1,0 +1,318 @@
+// K13 / K14: model-discrepancy kernel matrices and the fused dense reductions behind logposterior / logpost_deriv /
+// solve_posterior_covariance (ObsData.py:131-214, LinearSolver.py:351-367, 600-613, 659-681).
+#include "common.cuh"
+
+int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev);
+int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, int k, double* B, int64_t ldb);
+int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv);
+int logdet_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, double* out_dev);
+size_t potrf_dinv_doubles(int n);
+
+namespace {
+
+// squared distance the way scipy cdist(...)**2 produces it: sqrt of the running sum, then squared
+__device__ __forceinline__ double r2_pair(const double* __restrict__ X, const double* __restrict__ Y, int d, int i, int j) {
+    double dx = __dsub_rn(X[(int64_t)i * d], Y[(int64_t)j * d]);
+    double s = __dmul_rn(dx, dx);
+    for (int q = 1; q < d; ++q) {
+        double dq = __dsub_rn(X[(int64_t)i * d + q], Y[(int64_t)j * d + q]);
+        s = __dadd_rn(s, __dmul_rn(dq, dq));
+    }
+    double r = __dsqrt_rn(s);
+    return __dmul_rn(r, r);
+}
+
+// M[i][j] = K_eta(x1_i, x2_j) + delta_ij unc_i^2 + rho2 * Cu[min(i,j)][max(i,j)]      (unc, Cu: square case only)
+// (SciPy's cho_factor(..., lower=False) only reads the upper triangle of its argument, so the matrix the reference
+//  factorises is the symmetric completion of the upper triangle of rho^2 Cu + K + sigma^2 I; Cu itself is not exactly
+//  symmetric because G is not -- SURVEY finding 1.)
+// which: 0 -> K as above, 1 -> dK/dsigma = 2K (no unc, no Cu), 2 -> dK/dl = K r2 exp(-2l), 3 -> r2 (calc_r2)
+__global__ void kernel_matrix_kernel(int m, int n, int d, const double* __restrict__ X1, const double* __restrict__ X2,
+                                     double e2s, double em2l, const double* __restrict__ unc, int unc_is_vector,
+                                     double rho2, const double* __restrict__ Cu, int64_t ldcu, int which,
+                                     double* __restrict__ M, int64_t ldm) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= m || j >= n) return;
+    double r2 = r2_pair(X1, X2, d, i, j);
+    double kv = __dmul_rn(e2s, exp(__dmul_rn(__dmul_rn(-0.5, r2), em2l)));
+    double v;
+    if (which == 0) {
+        v = kv;
+        if (unc && i == j) {
+            double u = unc_is_vector ? unc[i] : unc[0];
+            v += u * u;
+        }
+        if (Cu) {
+            int a = i < j ? i : j, b = i < j ? j : i;
+            v = rho2 * Cu[(int64_t)a * ldcu + b] + v;
+        }
+    } else if (which == 1) {
+        v = 2.0 * kv;
+    } else if (which == 2) {
+        v = kv * r2 * em2l;
+    } else {
+        v = r2;
+    }
+    M[(int64_t)i * ldm + j] = v;
+}
+
+// z = a*x + b*y  (vectors)
+__global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                             double* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+
+// C = A + s * B  (n x n matrices, ld n)
+__global__ void mat_axpy_kernel(int64_t tot, const double* __restrict__ A, double s, const double* __restrict__ B,
+                                double* __restrict__ C) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tot) C[i] = A[i] + s * B[i];
+}
+
+// deterministic single-block dot products: out[q] = x_q . y_q
+struct DotJob { const double* x; const double* y; };
+__global__ void dots_kernel(int n, DotJob j0, DotJob j1, DotJob j2, double* __restrict__ out) {
+    __shared__ double sh[3][256];
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (j0.x) s0 += j0.x[i] * j0.y[i];
+        if (j1.x) s1 += j1.x[i] * j1.y[i];
+        if (j2.x) s2 += j2.x[i] * j2.y[i];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// Gradient reductions, one pass over the n x n index space, K and dK/dl evaluated on the fly:
+//   S0 = a^T Cu a, S1 = sum Kinv.*Cu, S2 = a^T K a, S3 = sum Kinv.*K, S4 = a^T dKl a, S5 = sum Kinv.*dKl
+__global__ void __launch_bounds__(256) grad_reduce_kernel(int n, int d, const double* __restrict__ X, double e2s,
+                                                          double em2l, const double* __restrict__ alpha,
+                                                          const double* __restrict__ Kinv, const double* __restrict__ Cu,
+                                                          double* __restrict__ partials) {
+    __shared__ double sh[6][256];
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    int64_t tot = (int64_t)n * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / n), j = (int)(t % n);
+        double r2 = r2_pair(X, X, d, i, j);
+        double kv = __dmul_rn(e2s, exp(__dmul_rn(__dmul_rn(-0.5, r2), em2l)));
+        double dkl = kv * r2 * em2l;
+        double aa = alpha[i] * alpha[j];
+        double ki = Kinv[t];
+        double cu = Cu[t];
+        s[0] += aa * cu; s[1] += ki * cu;
+        s[2] += aa * kv; s[3] += ki * kv;
+        s[4] += aa * dkl; s[5] += ki * dkl;
+    }
+    for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = s[q];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) partials[(int64_t)blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void grad_final_kernel(int nblk, const double* __restrict__ partials, double* __restrict__ out6) {
+    int q = threadIdx.x;
+    if (q >= 6) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partials[(int64_t)b * 6 + q];
+    out6[q] = s;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int build_matrix(sfem_ctx* c, int n, int d, const double* Xs, double sigma, double l, const double* unc, int unc_vec,
+                 double rho2, const double* Cu, int which, double* M) {
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
+    kernel_matrix_kernel<<<grd, blk, 0, c->stream>>>(n, n, d, Xs, Xs, exp(2.0 * sigma), exp(-2.0 * l), unc, unc_vec, rho2,
+                                                     Cu, n, which, M, n);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+}  // namespace
+
+int dense_kernel_matrix(sfem_ctx* c, int n, int d, const double* Xs, double sigma, double l, const double* unc,
+                        int unc_vec, double rho2, const double* Cu, int which, double* M) {
+    return build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, rho2, Cu, which, M);
+}
+
+// rectangular covariance block between two point sets (covariance_functions.py:4-77, 122-145)
+int dense_cov_matrix(sfem_ctx* c, int m, int n, int d, const double* X1, const double* X2, double sigma, double l, int which,
+                     double* M) {
+    if (m <= 0 || n <= 0) return SFEM_OK;
+    dim3 blk(32, 8), grd((n + 31) / 32, (m + 7) / 8);
+    kernel_matrix_kernel<<<grd, blk, 0, c->stream>>>(m, n, d, X1, X2, exp(2.0 * sigma), exp(-2.0 * l), nullptr, 0, 0.0,
+                                                     nullptr, 0, which, M, n);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+int dense_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z) {
+    if (n <= 0) return SFEM_OK;
+    axpby_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>((int)n, a, x, b, y, z);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+// workspace (doubles): M n^2 | W n^2 | Kinv n^2 | dinv | vectors 4n | partials | small
+size_t dense_workspace_bytes(int n) {
+    size_t nn = (size_t)n * n;
+    return align256(sizeof(double) * nn) * 3 + align256(sizeof(double) * potrf_dinv_doubles(n)) +
+           align256(sizeof(double) * 8 * (size_t)n) + align256(sizeof(double) * 6 * 4 * SFEM_NUM_SMS) + 4096;
+}
+
+struct DenseWs {
+    double *M, *W, *Kinv, *dinv, *vec, *partials, *small;
+    int* info;
+};
+static DenseWs carve(int n, void* work) {
+    DenseWs w;
+    unsigned char* p = (unsigned char*)work;
+    size_t nn = (size_t)n * n;
+    w.M = (double*)p; p += align256(sizeof(double) * nn);
+    w.W = (double*)p; p += align256(sizeof(double) * nn);
+    w.Kinv = (double*)p; p += align256(sizeof(double) * nn);
+    w.dinv = (double*)p; p += align256(sizeof(double) * potrf_dinv_doubles(n));
+    w.vec = (double*)p; p += align256(sizeof(double) * 8 * (size_t)n);
+    w.partials = (double*)p; p += align256(sizeof(double) * 6 * 4 * SFEM_NUM_SMS);
+    w.small = (double*)p;
+    w.info = (int*)(w.small + 64);
+    return w;
+}
+
+// value = 0.5 (n log 2pi + log|KCu| + r^T KCu^-1 r),  r = y - rho mu;  optional gradient (3 doubles).
+// theta = (log rho, log sigma_eta, log l_eta).  Returns SFEM_ERR_NOT_SPD if the factorisation breaks down.
+int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
+                  const double* mu, const double* Cu, const double* theta_host, double* value_host, double* grad_host,
+                  void* work, size_t work_bytes) {
+    if (work_bytes < dense_workspace_bytes(n)) return sfem_fail(c, SFEM_ERR_ARG, "logpost: workspace too small");
+    DenseWs w = carve(n, work);
+    double rho = exp(theta_host[0]);
+    double sigma = theta_host[1], l = theta_host[2];
+    double* r = w.vec;
+    double* alpha = w.vec + n;
+    int rc = build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, rho * rho, Cu, 0, w.M);
+    if (rc) return rc;
+    axpby_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 1.0, y, -rho, mu, r);
+    KCHECK(c);
+    CUDA_TRY(c, cudaMemcpyAsync(alpha, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
+    if (rc) return rc;
+    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, alpha, 1);
+    if (rc) return rc;
+    rc = logdet_lower(c, n, w.M, n, w.small + 8);
+    if (rc) return rc;
+    DotJob j0{r, alpha}, j1{mu, alpha}, jn{nullptr, nullptr};
+    dots_kernel<<<1, 256, 0, c->stream>>>(n, j0, j1, jn, w.small);
+    KCHECK(c);
+    if (grad_host) {
+        rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
+        if (rc) return rc;
+        int nblk = 4 * SFEM_NUM_SMS;
+        grad_reduce_kernel<<<nblk, 256, 0, c->stream>>>(n, d, Xs, exp(2.0 * sigma), exp(-2.0 * l), alpha, w.Kinv, Cu, w.partials);
+        KCHECK(c);
+        grad_final_kernel<<<1, 32, 0, c->stream>>>(nblk, w.partials, w.small + 16);
+        KCHECK(c);
+    }
+    double h[32];
+    int info = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(h, w.small, sizeof(double) * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (info != 0) return sfem_fail(c, SFEM_ERR_NOT_SPD, "logpost: covariance matrix not positive definite (pivot %d)", info);
+    const double LOG2PI = 1.8378770664093454835606594728112;
+    if (value_host) *value_host = 0.5 * ((double)n * LOG2PI + h[8] + h[0]);
+    if (grad_host) {
+        double mu_alpha = h[1];
+        const double* S = h + 16;
+        // LinearSolver.py:672-677
+        grad_host[0] = -rho * mu_alpha - rho * rho * S[0] + rho * rho * S[1];
+        grad_host[1] = -0.5 * (2.0 * S[2] - 2.0 * S[3]);
+        grad_host[2] = -0.5 * (S[4] - S[5]);
+    }
+    return SFEM_OK;
+}
+
+// solve_posterior_covariance (LinearSolver.py:351-367): muy (n) and Cuy (n x n) on the device.
+// workspace as dense_workspace_bytes(n).
+int dense_posterior_cov(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
+                        const double* mu, const double* Cu, const double* theta_host, double* muy_out, double* Cuy_out,
+                        void* work, size_t work_bytes) {
+    if (work_bytes < dense_workspace_bytes(n)) return sfem_fail(c, SFEM_ERR_ARG, "posterior_cov: workspace too small");
+    DenseWs w = carve(n, work);
+    double rho = exp(theta_host[0]);
+    double sigma = theta_host[1], l = theta_host[2];
+    double* t1 = w.vec;
+    double* muy = w.vec + n;
+    double* t2 = w.vec + 2 * n;
+    // Ks = K + sigma^2 I ; t1 = Ks^-1 y
+    int rc = build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, 0.0, nullptr, 0, w.M);
+    if (rc) return rc;
+    rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(t1, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, t1, 1);
+    if (rc) return rc;
+    int info1 = 0, info2 = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&info1, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // muy = rho Cu t1 + mu
+    CUDA_TRY(c, cudaMemcpyAsync(muy, mu, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = dgemm(c, OP_N, OP_N, n, 1, n, rho, Cu, n, t1, 1, 1.0, muy, 1, 0);
+    if (rc) return rc;
+    // LC = chol(Ks + rho^2 Cu)
+    rc = build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, rho * rho, Cu, 0, w.M);
+    if (rc) return rc;
+    rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(&info2, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // muy -= rho^2 Cu (LC^-1 muy)
+    CUDA_TRY(c, cudaMemcpyAsync(t2, muy, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, t2, 1);
+    if (rc) return rc;
+    rc = dgemm(c, OP_N, OP_N, n, 1, n, -rho * rho, Cu, n, t2, 1, 1.0, muy, 1, 0);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(muy_out, muy, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    // Cuy = Cu - rho^2 Cu (LC^-1 Cu)
+    CUDA_TRY(c, cudaMemcpyAsync(w.W, Cu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = potrs_lower(c, n, w.M, n, w.dinv, n, w.W, n);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(Cuy_out, Cu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = dgemm(c, OP_N, OP_N, n, n, n, -rho * rho, Cu, n, w.W, n, 1.0, Cuy_out, n, 0);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (info1 != 0 || info2 != 0)
+        return sfem_fail(c, SFEM_ERR_NOT_SPD, "Cholesky factorization of one of the covariance matrices failed");
+    return SFEM_OK;
+}
+
+// x = inv(M) b with M = K + unc^2 I + rho2 * sym_upper(Cu)   (the two dense solves inside solve_posterior,
+// LinearSolver.py:271-277 and 291-297).  b, x: device vectors of length n (may alias).
+int dense_solve_shifted(sfem_ctx* c, int n, int d, const double* Xs, const double* unc, int unc_vec, double sigma, double l,
+                        double rho2, const double* Cu, const double* b, double* x, void* work, size_t work_bytes) {
+    if (work_bytes < dense_workspace_bytes(n)) return sfem_fail(c, SFEM_ERR_ARG, "dense_solve: workspace too small");
+    DenseWs w = carve(n, work);
+    int rc = build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, rho2, Cu, 0, w.M);
+    if (rc) return rc;
+    rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
+    if (rc) return rc;
+    if (x != b) CUDA_TRY(c, cudaMemcpyAsync(x, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, x, 1);
+    if (rc) return rc;
+    int info = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (info != 0) return sfem_fail(c, SFEM_ERR_NOT_SPD, "Cholesky factorization failed (pivot %d)", info);
+    return SFEM_OK;
+}

@@ -1,0 +1,298 @@
+// K9: FP64 tensor-core GEMM for sm_100a.
+//
+//   C[M x N] = alpha * op(A) * op(B) + beta * C          (row-major everywhere)
+//
+// FP64 has no tcgen05/TMEM kind on Blackwell; the FP64 tensor path is mma.sync (DMMA.8x8x4 in SASS).  The
+// kernel is a 128x128x16 CTA tile, 8 warps (2 x 4), 64x32 warp tiles held in registers (64 doubles/thread),
+// a 4-stage cp.async (LDGSTS) global->shared pipeline, and bank-conflict-free padded shared layouts:
+//   k-major operand  (op(A)=A^T stored K x M, op(B)=B stored K x N):  tile [16][132]
+//   mn-major operand (op(A)=A   stored M x K, op(B)=B^T stored N x K): tile [128][20]
+// (132 = 4 mod 16 and 20 = 4 mod 16 doubles make the 16 lanes of a half-warp hit 16 distinct 8-byte banks
+//  for the (row = lane>>2, k = lane&3) fragment pattern of mma.m8n8k4.f64.)
+//
+// Users on the hot path: Cu = W^T Z (TN, K = n_dof: SURVEY K9), blocked Cholesky/TRSM/potri (chol.cu),
+// posterior covariance products (dense_ops.cu).  Reference call sites replaced: the per-sensor
+// P^T (A^-1 G A^-1 p_i) loop of solving_utils.py:139-142 and NumPy/LAPACK calls of LinearSolver.py:361-367.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
+constexpr int LDK = 132;            // k-major tile row stride (doubles)
+constexpr int LDMN = 20;            // mn-major tile row stride (doubles)
+constexpr int TILE_DOUBLES = 2560;  // max(16*132, 128*20)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double);
+
+struct GemmParams {
+    int M, N;
+    int64_t K;
+    const double* A; int64_t lda;
+    const double* B; int64_t ldb;
+    double* C; int64_t ldc;
+    double alpha, beta;
+    int lower_only;      // skip tiles strictly above the block diagonal
+    int tri_k;           // 1: k starts at max(m0, n0) (both operands lower-triangular "k >= index")
+    int64_t kchunk;      // split-K chunk (multiple of BK); gridDim.z chunks
+    double* partial;     // split-K workspace [gridDim.z][M][N] or nullptr
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// Load one operand tile for k-range [k0, k0+BK) (clipped to kend) and mn-range [mn0, mn0+128) (clipped to MN).
+// KM = true : source element (k, mn) at src[k*ld + mn]   -> smem[k*LDK + mn]
+// KM = false: source element (mn, k) at src[mn*ld + k]   -> smem[mn*LDMN + k]
+template <bool KM, bool AL16>
+__device__ __forceinline__ void load_tile(double* smem, const double* __restrict__ src, int64_t ld, int64_t k0,
+                                          int64_t kend, int mn0, int MN, int tid) {
+    if (KM) {
+        if (AL16) {
+#pragma unroll
+            for (int it = 0; it < (BK * 64) / NTHREADS; ++it) {
+                int q = tid + it * NTHREADS;
+                int row = q >> 6, c2 = (q & 63) * 2;
+                int64_t k = k0 + row;
+                int mn = mn0 + c2;
+                int valid = (k < kend) ? (mn + 1 < MN ? 16 : (mn < MN ? 8 : 0)) : 0;
+                const double* g = valid ? (src + k * ld + mn) : src;
+                cp_async_16(smem + row * LDK + c2, g, valid);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (BK * 128) / NTHREADS; ++it) {
+                int q = tid + it * NTHREADS;
+                int row = q >> 7, cc = q & 127;
+                int64_t k = k0 + row;
+                int mn = mn0 + cc;
+                int valid = (k < kend && mn < MN) ? 8 : 0;
+                const double* g = valid ? (src + k * ld + mn) : src;
+                cp_async_8(smem + row * LDK + cc, g, valid);
+            }
+        }
+    } else {
+        if (AL16) {
+#pragma unroll
+            for (int it = 0; it < (128 * 8) / NTHREADS; ++it) {
+                int q = tid + it * NTHREADS;
+                int row = q >> 3, c2 = (q & 7) * 2;
+                int64_t k = k0 + c2;
+                int mn = mn0 + row;
+                int valid = (mn < MN) ? (k + 1 < kend ? 16 : (k < kend ? 8 : 0)) : 0;
+                const double* g = valid ? (src + (int64_t)mn * ld + k) : src;
+                cp_async_16(smem + row * LDMN + c2, g, valid);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (128 * 16) / NTHREADS; ++it) {
+                int q = tid + it * NTHREADS;
+                int row = q >> 4, cc = q & 15;
+                int64_t k = k0 + cc;
+                int mn = mn0 + row;
+                int valid = (mn < MN && k < kend) ? 8 : 0;
+                const double* g = valid ? (src + (int64_t)mn * ld + k) : src;
+                cp_async_8(smem + row * LDMN + cc, g, valid);
+            }
+        }
+    }
+}
+
+template <bool AKM, bool BKM, bool AL16>
+__global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(GemmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    // tile rasterisation: strips of 8 tile-rows so concurrently resident CTAs share operand panels in L2
+    int tile = blockIdx.x;
+    const int GROUP = 8;
+    int tiles_per_group = GROUP * p.tiles_n;
+    int g = tile / tiles_per_group;
+    int first_m = g * GROUP;
+    int gsize = min(p.tiles_m - first_m, GROUP);
+    int tm = first_m + (tile % tiles_per_group) % gsize;
+    int tn = (tile % tiles_per_group) / gsize;
+    int m0 = tm * BM, n0 = tn * BN;
+    if (p.lower_only && n0 > m0) return;
+
+    int64_t kbeg = (int64_t)blockIdx.z * p.kchunk;
+    int64_t kend = kbeg + p.kchunk < p.K ? kbeg + p.kchunk : p.K;
+    if (p.tri_k) {
+        int64_t ks = m0 > n0 ? m0 : n0;     // multiples of 128 -> aligned to BK
+        if (ks > kbeg) kbeg = ks;
+    }
+    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+    int lr = lane >> 2, lk = lane & 3;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    int64_t nk = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+
+    auto issue = [&](int64_t kt) {
+        if (kt < nk) {
+            int slot = (int)(kt % STAGES);
+            double* sA = smem + (size_t)slot * 2 * TILE_DOUBLES;
+            double* sB = sA + TILE_DOUBLES;
+            int64_t k0 = kbeg + kt * BK;
+            load_tile<AKM, AL16>(sA, p.A, p.lda, k0, kend, m0, p.M, tid);
+            load_tile<BKM, AL16>(sB, p.B, p.ldb, k0, kend, n0, p.N, tid);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(kt + STAGES - 1);
+        const double* sA = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
+        const double* sB = sA + TILE_DOUBLES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double a[8], b[4];
+            int kk = ks * 4 + lk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int m = wm0 + i * 8 + lr;
+                a[i] = AKM ? sA[kk * LDK + m] : sA[m * LDMN + kk];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = wn0 + j * 8 + lr;
+                b[j] = BKM ? sB[kk * LDK + n] : sB[n * LDMN + kk];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue
+    if (p.partial) {
+        double* P = p.partial + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int m = m0 + wm0 + i * 8 + lr;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = n0 + wn0 + j * 8 + lk * 2;
+                if (n < p.N) P[(size_t)m * p.N + n] = acc[i][j][0];
+                if (n + 1 < p.N) P[(size_t)m * p.N + n + 1] = acc[i][j][1];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int m = m0 + wm0 + i * 8 + lr;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = n0 + wn0 + j * 8 + lk * 2;
+                double* c = p.C + (int64_t)m * p.ldc + n;
+                if (n < p.N) c[0] = p.alpha * acc[i][j][0] + (p.beta != 0.0 ? p.beta * c[0] : 0.0);
+                if (n + 1 < p.N) c[1] = p.alpha * acc[i][j][1] + (p.beta != 0.0 ? p.beta * c[1] : 0.0);
+            }
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(int M, int N, int splits, const double* __restrict__ partial, double alpha,
+                                     double beta, double* __restrict__ C, int64_t ldc, int lower_only) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    int m = (int)(idx / N), n = (int)(idx % N);
+    if (lower_only && (n / BN) > (m / BM)) return;
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * M * N + idx];
+    double* c = C + (int64_t)m * ldc + n;
+    *c = alpha * s + (beta != 0.0 ? beta * (*c) : 0.0);
+}
+
+template <bool AKM, bool BKM>
+int launch(sfem_ctx* c, const GemmParams& p, bool al16, dim3 grid) {
+    if (al16) {
+        auto k = dgemm_kernel<AKM, BKM, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        k<<<grid, NTHREADS, SMEM_BYTES, c->stream>>>(p);
+    } else {
+        auto k = dgemm_kernel<AKM, BKM, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        k<<<grid, NTHREADS, SMEM_BYTES, c->stream>>>(p);
+    }
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+}  // namespace
+
+// tri: 0 none, 1 = k starts at max(m0,n0) (used for Linv^T Linv).  Encoded in the high bits of lower_only:
+//   lower_only & 1 -> only tiles on/below the block diagonal, lower_only & 2 -> tri_k.
+int dgemm(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+    if (M <= 0 || N <= 0) return SFEM_OK;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta;
+    p.lower_only = flags & 1;
+    p.tri_k = (flags & 2) ? 1 : 0;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    p.partial = nullptr;
+    int tiles = p.tiles_m * p.tiles_n;
+    // split-K when the tile grid cannot fill the machine and K is long (e.g. Cu = W^T Z with few sensors)
+    int splits = 1;
+    if (!p.tri_k && tiles < SFEM_NUM_SMS && K >= 4096) {
+        splits = (2 * SFEM_NUM_SMS + tiles - 1) / tiles;
+        int64_t maxs = K / 1024;
+        if (splits > maxs) splits = (int)maxs;
+        if (splits < 1) splits = 1;
+    }
+    int64_t kchunk = K;
+    if (splits > 1) {
+        kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+        splits = (int)((K + kchunk - 1) / kchunk);
+        p.partial = (double*)sfem_scratch(c, (size_t)splits * M * N * sizeof(double));
+        if (!p.partial) return sfem_fail(c, SFEM_ERR_CUDA, "dgemm: split-K workspace allocation failed");
+    }
+    p.kchunk = kchunk > 0 ? kchunk : BK;
+    bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0) &&
+                (lda % 2 == 0) && (ldb % 2 == 0);
+    dim3 grid(tiles, 1, splits);
+    bool akm = (opA == OP_T), bkm = (opB == OP_N);
+    int rc;
+    if (akm && bkm) rc = launch<true, true>(c, p, al16, grid);
+    else if (akm && !bkm) rc = launch<true, false>(c, p, al16, grid);
+    else if (!akm && bkm) rc = launch<false, true>(c, p, al16, grid);
+    else rc = launch<false, false>(c, p, al16, grid);
+    if (rc) return rc;
+    if (splits > 1) {
+        int64_t tot = (int64_t)M * N;
+        splitk_reduce_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, c->stream>>>(M, N, splits, p.partial, alpha, beta,
+                                                                               C, ldc, p.lower_only);
+        KCHECK(c);
+    }
+    return SFEM_OK;
+}

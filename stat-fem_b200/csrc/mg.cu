@@ -1,0 +1,810 @@
+// K4: lattice multigrid V-cycle preconditioner for the stiffness matrix, built on the GPU from (CSR A, DOF
+// coordinates, Dirichlet mask).
+//
+// Hierarchy:  level 0 = the FEM matrix in CSR.  Level 1 = a regular lattice (2^p+1 nodes per direction, about half
+// the fine resolution) laid over the bounding box; fine DOFs interpolate multilinearly from the 2^d corners of the
+// lattice cell they sit in, whatever the mesh connectivity or DOF numbering is.  Levels 2.. = the lattice coarsened
+// by two per direction (standard multilinear transfer).  Every coarse operator is the Galerkin product P^T A P,
+// stored as a dense 5^d stencil per lattice node (enough for P1 meshes no coarser than the level-1 lattice).  The
+// coarsest lattice is inverted densely.  Smoother: damped Jacobi, nu sweeps before and after (symmetric, so the
+// V-cycle is an SPD preconditioner for CG).  All vectors are row-major multi-RHS blocks [n_level x k].
+//
+// This is the replacement for the sparse direct solve behind Firedrake's LinearSolver (LinearSolver.py:136-140,
+// solving_utils.py:51,53): unpreconditioned CG needs ~3.7*N_side iterations on these meshes (SURVEY finding 5).
+#include "rowops.cuh"
+#include <cmath>
+
+int build_cell_list(sfem_ctx* c, const int* cell_of, int64_t n, int ncell, int** cell_start_out, int** cell_nodes_out);
+int csr_jacobi(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
+               const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
+               const double* dinv, double omega);
+int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
+                 const double* X, int64_t ldx, double* R, int64_t ldr, const double* B, int64_t ldb);
+
+struct MGLevel {
+    int kind = 1;                 // 0 = CSR fine level, 1 = lattice
+    int64_t n = 0;
+    int d = 1;
+    int m[3] = {1, 1, 1};         // lattice nodes per direction
+    int S = 5;                    // stencil entries per node (5^d)
+    double* stencil = nullptr;    // [n][S]
+    double* dinv = nullptr;       // [n]
+    unsigned char* constrained = nullptr;   // [n]  (level 0: Dirichlet mask, owned copy)
+    // level 0 -> level 1 transfer
+    int* cidx = nullptr;          // [n] lattice cell of each fine node
+    double* frac = nullptr;       // [n][d] position inside the cell, in [0,1]
+    int* cell_start = nullptr;
+    int* cell_nodes = nullptr;
+    // lattice -> next lattice
+    int coarsen[3] = {0, 0, 0};
+    double* dense_inv = nullptr;  // coarsest: [n][n]
+};
+
+namespace {
+
+struct Lat {
+    int d, m0, m1, m2, S;
+    int64_t n;
+};
+__host__ __device__ inline Lat make_lat(int d, const int* m) {
+    Lat L;
+    L.d = d; L.m0 = m[0]; L.m1 = d > 1 ? m[1] : 1; L.m2 = d > 2 ? m[2] : 1;
+    L.S = d == 1 ? 5 : (d == 2 ? 25 : 125);
+    L.n = (int64_t)L.m0 * L.m1 * L.m2;
+    return L;
+}
+__device__ __forceinline__ void lat_decode(const Lat& L, int node, int& i0, int& i1, int& i2) {
+    i0 = node % L.m0;
+    int t = node / L.m0;
+    i1 = t % L.m1;
+    i2 = t / L.m1;
+}
+__device__ __forceinline__ int lat_index(const Lat& L, int i0, int i1, int i2) { return i0 + L.m0 * (i1 + L.m1 * i2); }
+// stencil slot <-> offset
+__device__ __forceinline__ int slot_of(int d, int o0, int o1, int o2) {
+    int s = o0 + 2;
+    if (d > 1) s += 5 * (o1 + 2);
+    if (d > 2) s += 25 * (o2 + 2);
+    return s;
+}
+__device__ __forceinline__ void slot_decode(int d, int s, int& o0, int& o1, int& o2) {
+    o0 = s % 5 - 2;
+    o1 = d > 1 ? (s / 5) % 5 - 2 : 0;
+    o2 = d > 2 ? s / 25 - 2 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------- setup kernels
+struct FineXfer {
+    int64_t n;
+    int d;
+    const double* coords;
+    double lo[3], invH[3];
+    Lat L1;
+};
+
+__global__ void fine_locate_kernel(FineXfer f, int* __restrict__ cidx, double* __restrict__ frac) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    int cc[3] = {0, 0, 0};
+    const int mm[3] = {f.L1.m0, f.L1.m1, f.L1.m2};
+    for (int k = 0; k < f.d; ++k) {
+        double u = (f.coords[i * f.d + k] - f.lo[k]) * f.invH[k];
+        int cell = (int)floor(u);
+        int maxc = mm[k] - 2;
+        if (cell < 0) cell = 0;
+        if (cell > maxc) cell = maxc;
+        double t = u - (double)cell;
+        t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+        cc[k] = cell;
+        frac[i * f.d + k] = t;
+    }
+    int mc0 = f.L1.m0 - 1, mc1 = f.d > 1 ? f.L1.m1 - 1 : 1;
+    cidx[i] = cc[0] + mc0 * (cc[1] + mc1 * cc[2]);
+}
+
+__global__ void csr_dinv_kernel(int64_t n, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                const double* __restrict__ val, double* __restrict__ dinv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double dg = 0.0;
+    for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p)
+        if (idx[p] == i) dg += val[p];
+    dinv[i] = dg != 0.0 ? 1.0 / dg : 1.0;
+}
+
+__device__ __forceinline__ double corner_weight(int d, const double* __restrict__ t, int beta) {
+    double w = (beta & 1) ? t[0] : 1.0 - t[0];
+    if (d > 1) w *= (beta & 2) ? t[1] : 1.0 - t[1];
+    if (d > 2) w *= (beta & 4) ? t[2] : 1.0 - t[2];
+    return w;
+}
+
+// level-1 lattice node is constrained iff its best-supported fine node is a Dirichlet node (or it has no support)
+__global__ void l1_constrained_kernel(Lat L, int d, const int* __restrict__ cell_start, const int* __restrict__ cell_nodes,
+                                      const double* __restrict__ frac, const unsigned char* __restrict__ bc,
+                                      unsigned char* __restrict__ constrained) {
+    int lane = threadIdx.x & 31;
+    int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (node >= L.n) return;
+    int i0, i1, i2;
+    lat_decode(L, node, i0, i1, i2);
+    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1, mc2 = d > 2 ? L.m2 - 1 : 1;
+    double wbc = 0.0, wfree = 0.0;
+    for (int beta = 0; beta < (1 << d); ++beta) {
+        int c0 = i0 - (beta & 1), c1 = i1 - ((beta >> 1) & 1), c2 = i2 - ((beta >> 2) & 1);
+        if (c0 < 0 || c0 >= mc0 || c1 < 0 || c1 >= mc1 || c2 < 0 || c2 >= mc2) continue;
+        int cell = c0 + mc0 * (c1 + mc1 * c2);
+        for (int q = cell_start[cell] + lane; q < cell_start[cell + 1]; q += 32) {
+            int i = cell_nodes[q];
+            double w = corner_weight(d, frac + (int64_t)i * d, beta);
+            if (bc[i]) wbc = fmax(wbc, w);
+            else wfree = fmax(wfree, w);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        wbc = fmax(wbc, __shfl_xor_sync(0xffffffffu, wbc, o));
+        wfree = fmax(wfree, __shfl_xor_sync(0xffffffffu, wfree, o));
+    }
+    if (lane == 0) constrained[node] = (wfree <= 0.0 || wbc >= wfree) ? 1 : 0;
+}
+
+// Galerkin product for level 1:  A1[I][J-I] = sum_{i,j} w_iI a_ij w_jJ  over free fine nodes i, j.
+// One warp per lattice node; every lane accumulates into its private column of a [S][32] shared array, the columns
+// are then summed in lane order (deterministic).  *err is set if a fine coupling reaches beyond the 5^d stencil.
+__global__ void l1_galerkin_kernel(Lat L, int d, int warps_per_block, const int64_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                   const int* __restrict__ cidx, const double* __restrict__ frac,
+                                   const unsigned char* __restrict__ bc, const int* __restrict__ cell_start,
+                                   const int* __restrict__ cell_nodes, const unsigned char* __restrict__ constrained,
+                                   double* __restrict__ stencil, int* __restrict__ err) {
+    extern __shared__ double acc_all[];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int node = blockIdx.x * warps_per_block + warp;
+    if (node >= L.n) return;
+    double* acc = acc_all + (size_t)warp * L.S * 32;
+    for (int s = 0; s < L.S; ++s) acc[s * 32 + lane] = 0.0;
+    int center = slot_of(d, 0, 0, 0);
+    if (constrained[node]) {
+        for (int s = lane; s < L.S; s += 32) stencil[(int64_t)node * L.S + s] = (s == center) ? 1.0 : 0.0;
+        return;
+    }
+    int i0, i1, i2;
+    lat_decode(L, node, i0, i1, i2);
+    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1, mc2 = d > 2 ? L.m2 - 1 : 1;
+    for (int beta = 0; beta < (1 << d); ++beta) {
+        int c0 = i0 - (beta & 1), c1 = i1 - ((beta >> 1) & 1), c2 = i2 - ((beta >> 2) & 1);
+        if (c0 < 0 || c0 >= mc0 || c1 < 0 || c1 >= mc1 || c2 < 0 || c2 >= mc2) continue;
+        int cell = c0 + mc0 * (c1 + mc1 * c2);
+        for (int q = cell_start[cell] + lane; q < cell_start[cell + 1]; q += 32) {
+            int i = cell_nodes[q];
+            if (bc[i]) continue;
+            double wi = corner_weight(d, frac + (int64_t)i * d, beta);
+            if (wi == 0.0) continue;
+            for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) {
+                int j = idx[p];
+                if (bc[j]) continue;
+                double a = val[p] * wi;
+                if (a == 0.0) continue;
+                int cj = cidx[j];
+                int j0 = cj % mc0, tq = cj / mc0;
+                int j1 = tq % mc1, j2 = tq / mc1;
+                const double* tj = frac + (int64_t)j * d;
+                for (int g = 0; g < (1 << d); ++g) {
+                    int J0 = j0 + (g & 1), J1 = j1 + ((g >> 1) & 1), J2 = j2 + ((g >> 2) & 1);
+                    double wj = corner_weight(d, tj, g);
+                    if (wj == 0.0) continue;
+                    if (constrained[lat_index(L, J0, J1, J2)]) continue;
+                    int o0 = J0 - i0, o1 = J1 - i1, o2 = J2 - i2;
+                    if (o0 < -2 || o0 > 2 || o1 < -2 || o1 > 2 || o2 < -2 || o2 > 2) {
+                        *err = 1;
+                        continue;
+                    }
+                    acc[slot_of(d, o0, o1, o2) * 32 + lane] += a * wj;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int s = lane; s < L.S; s += 32) {
+        double t = 0.0;
+        for (int l = 0; l < 32; ++l) t += acc[s * 32 + l];
+        stencil[(int64_t)node * L.S + s] = t;
+    }
+}
+
+// lattice -> coarser lattice
+struct LatPair {
+    Lat F, C;
+    int d;
+    int co[3];     // direction coarsened?
+};
+
+__global__ void lat_constrained_kernel(LatPair P, const unsigned char* __restrict__ cf, unsigned char* __restrict__ cc) {
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= P.C.n) return;
+    int I0, I1, I2;
+    lat_decode(P.C, node, I0, I1, I2);
+    int f0 = P.co[0] ? 2 * I0 : I0, f1 = P.co[1] ? 2 * I1 : I1, f2 = P.co[2] ? 2 * I2 : I2;
+    cc[node] = cf[lat_index(P.F, f0, f1, f2)];
+}
+
+__device__ __forceinline__ double w1d(int co, int e) { return co ? (e == 0 ? 1.0 : 0.5) : 1.0; }
+
+// Galerkin for lattice levels: one thread per (coarse node, coarse offset)
+__global__ void lat_galerkin_kernel(LatPair P, const double* __restrict__ sf, const unsigned char* __restrict__ cf,
+                                    const unsigned char* __restrict__ cc, double* __restrict__ sc) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int S = P.C.S;
+    if (tid >= P.C.n * S) return;
+    int node = (int)(tid / S), slot = (int)(tid % S);
+    int d = P.d;
+    int center = slot_of(d, 0, 0, 0);
+    if (cc[node]) {
+        sc[tid] = (slot == center) ? 1.0 : 0.0;
+        return;
+    }
+    int D0, D1, D2;
+    slot_decode(d, slot, D0, D1, D2);
+    int I0, I1, I2;
+    lat_decode(P.C, node, I0, I1, I2);
+    int J0 = I0 + D0, J1 = I1 + D1, J2 = I2 + D2;
+    if (J0 < 0 || J0 >= P.C.m0 || J1 < 0 || J1 >= P.C.m1 || J2 < 0 || J2 >= P.C.m2 || cc[lat_index(P.C, J0, J1, J2)]) {
+        sc[tid] = 0.0;
+        return;
+    }
+    int r0 = P.co[0] ? 1 : 0, r1 = (d > 1 && P.co[1]) ? 1 : 0, r2 = (d > 2 && P.co[2]) ? 1 : 0;
+    int s0 = P.co[0] ? 2 : 1, s1 = P.co[1] ? 2 : 1, s2 = P.co[2] ? 2 : 1;
+    double total = 0.0;
+    for (int e2 = -r2; e2 <= r2; ++e2)
+        for (int e1 = -r1; e1 <= r1; ++e1)
+            for (int e0 = -r0; e0 <= r0; ++e0) {
+                int i0 = s0 * I0 + e0, i1 = s1 * I1 + e1, i2 = s2 * I2 + e2;
+                if (i0 < 0 || i0 >= P.F.m0 || i1 < 0 || i1 >= P.F.m1 || i2 < 0 || i2 >= P.F.m2) continue;
+                int fi = lat_index(P.F, i0, i1, i2);
+                if (cf[fi]) continue;
+                double we = w1d(P.co[0], e0) * w1d(P.co[1], e1) * w1d(P.co[2], e2);
+                const double* row = sf + (int64_t)fi * P.F.S;
+                for (int f2 = -r2; f2 <= r2; ++f2)
+                    for (int f1 = -r1; f1 <= r1; ++f1)
+                        for (int f0 = -r0; f0 <= r0; ++f0) {
+                            int j0 = s0 * J0 + f0, j1 = s1 * J1 + f1, j2 = s2 * J2 + f2;
+                            if (j0 < 0 || j0 >= P.F.m0 || j1 < 0 || j1 >= P.F.m1 || j2 < 0 || j2 >= P.F.m2) continue;
+                            int o0 = j0 - i0, o1 = j1 - i1, o2 = j2 - i2;
+                            if (o0 < -2 || o0 > 2 || o1 < -2 || o1 > 2 || o2 < -2 || o2 > 2) continue;
+                            if (cf[lat_index(P.F, j0, j1, j2)]) continue;
+                            double a = row[slot_of(d, o0, o1, o2)];
+                            if (a != 0.0) total += we * a * w1d(P.co[0], f0) * w1d(P.co[1], f1) * w1d(P.co[2], f2);
+                        }
+            }
+    sc[tid] = total;
+}
+
+// dinv[i] = omega / a_ii on free nodes, 1 on constrained (identity) rows so those are solved exactly by one sweep
+__global__ void lat_dinv_kernel(int64_t n, int S, int center, double omega, double* __restrict__ stencil,
+                                double* __restrict__ dinv, unsigned char* __restrict__ constrained) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double dg = stencil[i * S + center];
+    if (!(dg > 0.0)) {   // unsupported lattice node: make it an identity row
+        for (int s = 0; s < S; ++s) stencil[i * S + s] = (s == center) ? 1.0 : 0.0;
+        constrained[i] = 1;
+        dg = 1.0;
+    }
+    dinv[i] = constrained[i] ? 1.0 / dg : omega / dg;
+}
+
+__global__ void fine_wdinv_kernel(int64_t n, double omega, const double* __restrict__ dinv,
+                                  const unsigned char* __restrict__ bc, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bc[i] ? dinv[i] : omega * dinv[i];
+}
+
+// dense matrix of the coarsest lattice operator
+__global__ void lat_to_dense_kernel(Lat L, int d, const double* __restrict__ stencil, double* __restrict__ D) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= L.n * L.S) return;
+    int node = (int)(tid / L.S), slot = (int)(tid % L.S);
+    double a = stencil[tid];
+    if (a == 0.0) return;
+    int o0, o1, o2, i0, i1, i2;
+    slot_decode(d, slot, o0, o1, o2);
+    lat_decode(L, node, i0, i1, i2);
+    int j = lat_index(L, i0 + o0, i1 + o1, i2 + o2);
+    D[(int64_t)node * L.n + j] = a;
+}
+
+// in-place Gauss-Jordan inverse of an SPD matrix (no pivoting), single CTA
+__global__ void dense_inverse_kernel(int n, double* __restrict__ A) {
+    __shared__ double piv;
+    extern __shared__ double colk[];   // n doubles
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) piv = 1.0 / A[(int64_t)k * n + k];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) colk[i] = A[(int64_t)i * n + k];
+        __syncthreads();
+        double p = piv;
+        // row k scaled
+        for (int j = threadIdx.x; j < n; j += blockDim.x) A[(int64_t)k * n + j] = (j == k) ? p : A[(int64_t)k * n + j] * p;
+        __syncthreads();
+        for (int64_t t = threadIdx.x; t < (int64_t)n * n; t += blockDim.x) {
+            int i = (int)(t / n), j = (int)(t % n);
+            if (i == k) continue;
+            double f = colk[i];
+            double akj = A[(int64_t)k * n + j];
+            A[t] = (j == k) ? -f * p : A[t] - f * akj;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- cycle kernels
+// x = omega * dinv .* b   (first smoothing sweep from a zero guess); constrained/identity rows give x = omega*b: the
+// coarse right-hand sides are zero there.  Generic over levels.
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) jacobi0_kernel(int64_t n, int k, const double* __restrict__ B, int64_t ldb,
+                                                            double* __restrict__ X, int64_t ldx,
+                                                            const double* __restrict__ dinv, double omega,
+                                                            int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double b0, b1;
+        ld_cols<VEC>(B + row * ldb, L, b0, b1);
+        double w = omega * dinv[row];
+        st_cols<VEC>(X + row * ldx, L, w * b0, w * b1);
+    }
+}
+
+enum { LM_JACOBI = 0, LM_RESID = 1 };
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(RB_THREADS) lat_block_kernel(Lat L, int d, const double* __restrict__ stencil, int k,
+                                                              const double* __restrict__ X, double* __restrict__ Y,
+                                                              const double* __restrict__ B,
+                                                              const double* __restrict__ dinv, double omega,
+                                                              int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < L.n ? r0 + rows_per_block : L.n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        const double* srow = stencil + row * L.S;
+        double a0 = 0.0, a1 = 0.0;
+        for (int s = 0; s < L.S; ++s) {
+            double a = srow[s];
+            if (a == 0.0) continue;
+            int o0, o1, o2;
+            slot_decode(d, s, o0, o1, o2);
+            int64_t nb = row + o0 + (int64_t)L.m0 * (o1 + (int64_t)L.m1 * o2);
+            double x0, x1;
+            ld_cols<VEC>(X + nb * k, C, x0, x1);
+            a0 += a * x0; a1 += a * x1;
+        }
+        double b0, b1;
+        ld_cols<VEC>(B + row * k, C, b0, b1);
+        if (MODE == LM_JACOBI) {
+            double x0, x1;
+            ld_cols<VEC>(X + row * k, C, x0, x1);
+            double w = omega * dinv[row];
+            a0 = x0 + w * (b0 - a0); a1 = x1 + w * (b1 - a1);
+        } else {
+            a0 = b0 - a0; a1 = b1 - a1;
+        }
+        st_cols<VEC>(Y + row * k, C, a0, a1);
+    }
+}
+
+// b1[I] = sum_i w_iI r[i]   (fine CSR level -> level-1 lattice); warp per lattice node
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) fine_restrict_kernel(Lat L, int d, int k, const double* __restrict__ R, int64_t ldr,
+                                                                  double* __restrict__ Bc, const int* __restrict__ cell_start,
+                                                                  const int* __restrict__ cell_nodes,
+                                                                  const double* __restrict__ frac,
+                                                                  const unsigned char* __restrict__ bc,
+                                                                  const unsigned char* __restrict__ constrained,
+                                                                  int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < L.n ? r0 + rows_per_block : L.n;
+    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1, mc2 = d > 2 ? L.m2 - 1 : 1;
+    for (int64_t node = r0 + warp; node < r1; node += RB_WARPS) {
+        double a0 = 0.0, a1 = 0.0;
+        if (!constrained[node]) {
+            int i0, i1, i2;
+            lat_decode(L, (int)node, i0, i1, i2);
+            for (int beta = 0; beta < (1 << d); ++beta) {
+                int c0 = i0 - (beta & 1), c1 = i1 - ((beta >> 1) & 1), c2 = i2 - ((beta >> 2) & 1);
+                if (c0 < 0 || c0 >= mc0 || c1 < 0 || c1 >= mc1 || c2 < 0 || c2 >= mc2) continue;
+                int cell = c0 + mc0 * (c1 + mc1 * c2);
+                for (int q = cell_start[cell]; q < cell_start[cell + 1]; ++q) {
+                    int i = cell_nodes[q];
+                    if (bc[i]) continue;
+                    double w = corner_weight(d, frac + (int64_t)i * d, beta);
+                    if (w == 0.0) continue;
+                    double x0, x1;
+                    ld_cols<VEC>(R + (int64_t)i * ldr, C, x0, x1);
+                    a0 += w * x0; a1 += w * x1;
+                }
+            }
+        }
+        st_cols<VEC>(Bc + node * k, C, a0, a1);
+    }
+}
+
+// x[i] += sum_corners w x1[I]   (level-1 lattice -> fine); warp per fine node
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) fine_prolong_kernel(int64_t n, Lat L, int d, int k, double* __restrict__ X, int64_t ldx,
+                                                                 const double* __restrict__ Xc, const int* __restrict__ cidx,
+                                                                 const double* __restrict__ frac,
+                                                                 const unsigned char* __restrict__ bc, int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1;
+    for (int64_t i = r0 + warp; i < r1; i += RB_WARPS) {
+        if (bc[i]) continue;
+        int cj = cidx[i];
+        int j0 = cj % mc0, tq = cj / mc0;
+        int j1 = tq % mc1, j2 = tq / mc1;
+        double a0, a1;
+        ld_cols<VEC>(X + i * ldx, C, a0, a1);
+        for (int g = 0; g < (1 << d); ++g) {
+            double w = corner_weight(d, frac + i * d, g);
+            if (w == 0.0) continue;
+            int64_t I = lat_index(L, j0 + (g & 1), j1 + ((g >> 1) & 1), j2 + ((g >> 2) & 1));
+            double x0, x1;
+            ld_cols<VEC>(Xc + I * k, C, x0, x1);
+            a0 += w * x0; a1 += w * x1;
+        }
+        st_cols<VEC>(X + i * ldx, C, a0, a1);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) lat_restrict_kernel(LatPair P, int k, const double* __restrict__ R,
+                                                                 double* __restrict__ Bc, const unsigned char* __restrict__ cf,
+                                                                 const unsigned char* __restrict__ cc, int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < P.C.n ? r0 + rows_per_block : P.C.n;
+    int d = P.d;
+    int q0 = P.co[0] ? 1 : 0, q1 = (d > 1 && P.co[1]) ? 1 : 0, q2 = (d > 2 && P.co[2]) ? 1 : 0;
+    int s0 = P.co[0] ? 2 : 1, s1 = P.co[1] ? 2 : 1, s2 = P.co[2] ? 2 : 1;
+    for (int64_t node = r0 + warp; node < r1; node += RB_WARPS) {
+        double a0 = 0.0, a1 = 0.0;
+        if (!cc[node]) {
+            int I0, I1, I2;
+            lat_decode(P.C, (int)node, I0, I1, I2);
+            for (int e2 = -q2; e2 <= q2; ++e2)
+                for (int e1 = -q1; e1 <= q1; ++e1)
+                    for (int e0 = -q0; e0 <= q0; ++e0) {
+                        int i0 = s0 * I0 + e0, i1 = s1 * I1 + e1, i2 = s2 * I2 + e2;
+                        if (i0 < 0 || i0 >= P.F.m0 || i1 < 0 || i1 >= P.F.m1 || i2 < 0 || i2 >= P.F.m2) continue;
+                        int64_t fi = lat_index(P.F, i0, i1, i2);
+                        if (cf[fi]) continue;
+                        double w = w1d(P.co[0], e0) * w1d(P.co[1], e1) * w1d(P.co[2], e2);
+                        double x0, x1;
+                        ld_cols<VEC>(R + fi * k, C, x0, x1);
+                        a0 += w * x0; a1 += w * x1;
+                    }
+        }
+        st_cols<VEC>(Bc + node * k, C, a0, a1);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) lat_prolong_kernel(LatPair P, int k, double* __restrict__ X,
+                                                                const double* __restrict__ Xc,
+                                                                const unsigned char* __restrict__ cf, int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < P.F.n ? r0 + rows_per_block : P.F.n;
+    for (int64_t fi = r0 + warp; fi < r1; fi += RB_WARPS) {
+        if (cf[fi]) continue;
+        int i[3];
+        lat_decode(P.F, (int)fi, i[0], i[1], i[2]);
+        int base[3], cnt[3];
+        double w[3];
+        for (int q = 0; q < 3; ++q) {
+            if (q < P.d && P.co[q]) {
+                if (i[q] & 1) { base[q] = (i[q] - 1) >> 1; cnt[q] = 2; w[q] = 0.5; }
+                else { base[q] = i[q] >> 1; cnt[q] = 1; w[q] = 1.0; }
+            } else { base[q] = i[q]; cnt[q] = 1; w[q] = 1.0; }
+        }
+        double a0, a1;
+        ld_cols<VEC>(X + fi * k, C, a0, a1);
+        for (int c2 = 0; c2 < cnt[2]; ++c2)
+            for (int c1 = 0; c1 < cnt[1]; ++c1)
+                for (int c0 = 0; c0 < cnt[0]; ++c0) {
+                    int64_t I = lat_index(P.C, base[0] + c0, base[1] + c1, base[2] + c2);
+                    double x0, x1;
+                    ld_cols<VEC>(Xc + I * k, C, x0, x1);
+                    double ww = w[0] * w[1] * w[2];
+                    a0 += ww * x0; a1 += ww * x1;
+                }
+        st_cols<VEC>(X + fi * k, C, a0, a1);
+    }
+}
+
+// x = Ainv b on the coarsest lattice (dense)
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) dense_apply_kernel(int n, int k, const double* __restrict__ Ainv,
+                                                                const double* __restrict__ B, double* __restrict__ X,
+                                                                int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> C(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int j = 0; j < n; ++j) {
+            double a = Ainv[row * n + j];
+            if (a == 0.0) continue;
+            double x0, x1;
+            ld_cols<VEC>(B + (int64_t)j * k, C, x0, x1);
+            a0 += a * x0; a1 += a * x1;
+        }
+        st_cols<VEC>(X + row * k, C, a0, a1);
+    }
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+LatPair make_pair(const MGLevel* F, const MGLevel* C) {
+    LatPair P;
+    P.F = make_lat(F->d, F->m);
+    P.C = make_lat(C->d, C->m);
+    P.d = F->d;
+    for (int q = 0; q < 3; ++q) P.co[q] = F->coarsen[q];
+    return P;
+}
+
+}  // namespace
+
+void mg_free(sfem_ctx* c) {
+    for (MGLevel* L : c->mg) {
+        if (L->stencil) cudaFree(L->stencil);
+        if (L->dinv) cudaFree(L->dinv);
+        if (L->constrained) cudaFree(L->constrained);
+        if (L->cidx) cudaFree(L->cidx);
+        if (L->frac) cudaFree(L->frac);
+        if (L->cell_start) cudaFree(L->cell_start);
+        if (L->cell_nodes) cudaFree(L->cell_nodes);
+        if (L->dense_inv) cudaFree(L->dense_inv);
+        delete L;
+    }
+    c->mg.clear();
+}
+
+int stiffness_dinv(sfem_ctx* c) {
+    if (c->A_dinv) cudaFree(c->A_dinv);
+    CUDA_TRY(c, cudaMalloc(&c->A_dinv, sizeof(double) * (size_t)c->n));
+    csr_dinv_kernel<<<(unsigned)cdiv64(c->n, 256), 256, 0, c->stream>>>(c->n, c->A_ptr, c->A_idx, c->A_val, c->A_dinv);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc_mask, const double* lo, const double* hi,
+             const int* m1, int nu, double omega, int max_coarse) {
+    if (!c->A_ptr) return sfem_fail(c, SFEM_ERR_STATE, "mg_setup: stiffness matrix not set");
+    if (dim < 1 || dim > 3) return sfem_fail(c, SFEM_ERR_ARG, "mg_setup: dimension must be 1, 2 or 3");
+    mg_free(c);
+    c->mg_nu_pre = c->mg_nu_post = nu < 1 ? 1 : nu;
+    c->mg_omega = omega;
+    int64_t n = c->n;
+    // ---- level 0
+    MGLevel* L0 = new MGLevel();
+    c->mg.push_back(L0);
+    L0->kind = 0; L0->n = n; L0->d = dim;
+    CUDA_TRY(c, cudaMalloc(&L0->constrained, (size_t)n));
+    CUDA_TRY(c, cudaMemcpyAsync(L0->constrained, bc_mask, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaMalloc(&L0->dinv, sizeof(double) * (size_t)n));
+    fine_wdinv_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(n, omega, c->A_dinv, L0->constrained, L0->dinv);
+    KCHECK(c);
+    CUDA_TRY(c, cudaMalloc(&L0->cidx, sizeof(int) * (size_t)n));
+    CUDA_TRY(c, cudaMalloc(&L0->frac, sizeof(double) * (size_t)n * dim));
+    // ---- level 1 lattice
+    MGLevel* L1 = new MGLevel();
+    c->mg.push_back(L1);
+    L1->d = dim;
+    for (int q = 0; q < 3; ++q) L1->m[q] = q < dim ? (m1[q] < 2 ? 2 : m1[q]) : 1;
+    Lat lat1 = make_lat(dim, L1->m);
+    L1->n = lat1.n; L1->S = lat1.S;
+    if (lat1.n > (int64_t)1 << 30) return sfem_fail(c, SFEM_ERR_LIMIT, "mg_setup: level-1 lattice too large");
+    FineXfer fx;
+    fx.n = n; fx.d = dim; fx.coords = coords; fx.L1 = lat1;
+    int64_t ncell = 1;
+    for (int q = 0; q < 3; ++q) {
+        fx.lo[q] = q < dim ? lo[q] : 0.0;
+        double ext = q < dim ? hi[q] - lo[q] : 1.0;
+        fx.invH[q] = (q < dim && ext > 0.0) ? (double)(L1->m[q] - 1) / ext : 0.0;
+        if (q < dim) ncell *= (L1->m[q] - 1);
+    }
+    fine_locate_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(fx, L0->cidx, L0->frac);
+    KCHECK(c);
+    int rc = build_cell_list(c, L0->cidx, n, (int)ncell, &L0->cell_start, &L0->cell_nodes);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMalloc(&L1->constrained, (size_t)lat1.n));
+    CUDA_TRY(c, cudaMalloc(&L1->stencil, sizeof(double) * (size_t)lat1.n * lat1.S));
+    CUDA_TRY(c, cudaMalloc(&L1->dinv, sizeof(double) * (size_t)lat1.n));
+    l1_constrained_kernel<<<(unsigned)cdiv64(lat1.n, 4), 128, 0, c->stream>>>(lat1, dim, L0->cell_start, L0->cell_nodes,
+                                                                             L0->frac, L0->constrained, L1->constrained);
+    KCHECK(c);
+    int* err = (int*)sfem_scratch(c, 64);
+    CUDA_TRY(c, cudaMemsetAsync(err, 0, sizeof(int), c->stream));
+    {
+        int wpb = dim == 3 ? 4 : 8;
+        size_t dyn = sizeof(double) * (size_t)wpb * lat1.S * 32;
+        cudaFuncSetAttribute(l1_galerkin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        l1_galerkin_kernel<<<(unsigned)cdiv64(lat1.n, wpb), wpb * 32, dyn, c->stream>>>(
+            lat1, dim, wpb, c->A_ptr, c->A_idx, c->A_val, L0->cidx, L0->frac, L0->constrained, L0->cell_start,
+            L0->cell_nodes, L1->constrained, L1->stencil, err);
+        KCHECK(c);
+    }
+    int herr = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (herr) return sfem_fail(c, SFEM_ERR_LIMIT, "mg_setup: mesh edges span more than one level-1 lattice cell; use a finer lattice");
+    int center = dim == 1 ? 2 : (dim == 2 ? 12 : 62);
+    lat_dinv_kernel<<<(unsigned)cdiv64(lat1.n, 256), 256, 0, c->stream>>>(lat1.n, lat1.S, center, omega, L1->stencil, L1->dinv, L1->constrained);
+    KCHECK(c);
+    // ---- coarser lattices
+    MGLevel* F = L1;
+    while (F->n > max_coarse) {
+        bool any = false;
+        MGLevel* C = new MGLevel();
+        C->d = dim;
+        for (int q = 0; q < 3; ++q) {
+            if (q < dim && F->m[q] >= 5 && (F->m[q] & 1)) {
+                F->coarsen[q] = 1;
+                C->m[q] = (F->m[q] + 1) / 2;
+                any = true;
+            } else {
+                F->coarsen[q] = 0;
+                C->m[q] = F->m[q];
+            }
+        }
+        if (!any) { delete C; break; }
+        c->mg.push_back(C);
+        Lat lc = make_lat(dim, C->m);
+        C->n = lc.n; C->S = lc.S;
+        CUDA_TRY(c, cudaMalloc(&C->constrained, (size_t)lc.n));
+        CUDA_TRY(c, cudaMalloc(&C->stencil, sizeof(double) * (size_t)lc.n * lc.S));
+        CUDA_TRY(c, cudaMalloc(&C->dinv, sizeof(double) * (size_t)lc.n));
+        LatPair P = make_pair(F, C);
+        lat_constrained_kernel<<<(unsigned)cdiv64(lc.n, 256), 256, 0, c->stream>>>(P, F->constrained, C->constrained);
+        KCHECK(c);
+        lat_galerkin_kernel<<<(unsigned)cdiv64(lc.n * lc.S, 128), 128, 0, c->stream>>>(P, F->stencil, F->constrained, C->constrained, C->stencil);
+        KCHECK(c);
+        lat_dinv_kernel<<<(unsigned)cdiv64(lc.n, 256), 256, 0, c->stream>>>(lc.n, lc.S, center, omega, C->stencil, C->dinv, C->constrained);
+        KCHECK(c);
+        F = C;
+    }
+    // ---- dense inverse on the coarsest lattice
+    if (F->n <= 1200) {
+        Lat lc = make_lat(dim, F->m);
+        int nn = (int)lc.n;
+        CUDA_TRY(c, cudaMalloc(&F->dense_inv, sizeof(double) * (size_t)nn * nn));
+        CUDA_TRY(c, cudaMemsetAsync(F->dense_inv, 0, sizeof(double) * (size_t)nn * nn, c->stream));
+        lat_to_dense_kernel<<<(unsigned)cdiv64(lc.n * lc.S, 256), 256, 0, c->stream>>>(lc, dim, F->stencil, F->dense_inv);
+        KCHECK(c);
+        dense_inverse_kernel<<<1, 1024, sizeof(double) * nn, c->stream>>>(nn, F->dense_inv);
+        KCHECK(c);
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SFEM_OK;
+}
+
+// workspace: for every lattice level: bufA, bufB, b  (each n_l x k)
+size_t mg_workspace_bytes(sfem_ctx* c, int k) {
+    size_t bytes = 0;
+    for (size_t l = 1; l < c->mg.size(); ++l) bytes += 3 * align256(sizeof(double) * (size_t)c->mg[l]->n * k);
+    return bytes + 256;
+}
+
+int mg_num_levels(sfem_ctx* c) { return (int)c->mg.size(); }
+int64_t mg_level_size(sfem_ctx* c, int l) { return (l >= 0 && l < (int)c->mg.size()) ? c->mg[l]->n : -1; }
+
+#define MG_LAUNCH(nrows, kern, ...)                                                                  \
+    do {                                                                                             \
+        RowGrid _g = row_grid(nrows);                                                                \
+        if (v2) kern<2> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
+        else kern<1> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
+        KCHECK(c);                                                                                   \
+    } while (0)
+#define MG_LAUNCH2(nrows, kern, MODE, ...)                                                           \
+    do {                                                                                             \
+        RowGrid _g = row_grid(nrows);                                                                \
+        if (v2) kern<2, MODE> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
+        else kern<1, MODE> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
+        KCHECK(c);                                                                                   \
+    } while (0)
+
+// Z = M^-1 R  (one V-cycle).  R: [n x k] ld ldr.  Z: ld ldz.  tmp0: [n x k] ld k (scratch on the fine level).
+int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_t ldz, double* tmp0, void* work) {
+    int nl = (int)c->mg.size();
+    if (nl < 2) return sfem_fail(c, SFEM_ERR_STATE, "mg_apply: hierarchy not built");
+    const int nu = c->mg_nu_pre;
+    const double om = 1.0;   // the damping factor is folded into the per-level dinv arrays (exact on identity rows)
+    bool v2 = (k % 2 == 0) && (ldr % 2 == 0) && (ldz % 2 == 0) &&
+              ((reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(tmp0)) % 16 == 0);
+    // carve lattice-level buffers
+    std::vector<double*> bufA(nl), bufB(nl), rhs(nl);
+    unsigned char* w = (unsigned char*)work;
+    for (int l = 1; l < nl; ++l) {
+        size_t sz = align256(sizeof(double) * (size_t)c->mg[l]->n * k);
+        bufA[l] = (double*)w; w += sz;
+        bufB[l] = (double*)w; w += sz;
+        rhs[l] = (double*)w; w += sz;
+    }
+    std::vector<double*> xcur(nl);
+    std::vector<int64_t> xld(nl);
+    MGLevel* L0 = c->mg[0];
+    int64_t n = L0->n;
+    // ---------------- level 0, downward.  2*nu - 1 buffer swaps in total: start in tmp0, finish in Z.
+    double* cur = tmp0; int64_t ldc = k;
+    double* oth = Z; int64_t ldo = ldz;
+    auto swap0 = [&]() { std::swap(cur, oth); std::swap(ldc, ldo); };
+    MG_LAUNCH(n, jacobi0_kernel, n, k, R, ldr, cur, ldc, L0->dinv, om);
+    for (int s = 1; s < nu; ++s) {
+        int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
+        if (rc) return rc;
+        swap0();
+    }
+    {
+        int rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr);
+        if (rc) return rc;
+    }
+    Lat lat1 = make_lat(c->mg[1]->d, c->mg[1]->m);
+    MG_LAUNCH(lat1.n, fine_restrict_kernel, lat1, L0->d, k, oth, ldo, rhs[1], L0->cell_start, L0->cell_nodes, L0->frac,
+              L0->constrained, c->mg[1]->constrained);
+    // ---------------- lattice levels, downward
+    for (int l = 1; l < nl; ++l) {
+        MGLevel* L = c->mg[l];
+        Lat lat = make_lat(L->d, L->m);
+        if (l == nl - 1 && L->dense_inv) {
+            MG_LAUNCH(lat.n, dense_apply_kernel, (int)lat.n, k, L->dense_inv, rhs[l], bufA[l]);
+            xcur[l] = bufA[l];
+            break;
+        }
+        double* a = bufA[l];
+        double* b = bufB[l];
+        MG_LAUNCH(lat.n, jacobi0_kernel, lat.n, k, rhs[l], (int64_t)k, a, (int64_t)k, L->dinv, om);
+        int sweeps = (l == nl - 1) ? 8 * nu : nu;    // no dense inverse available: smooth harder on the last level
+        for (int s = 1; s < sweeps; ++s) {
+            MG_LAUNCH2(lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+            std::swap(a, b);
+        }
+        xcur[l] = a;
+        if (l == nl - 1) break;
+        MG_LAUNCH2(lat.n, lat_block_kernel, LM_RESID, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+        LatPair P = make_pair(L, c->mg[l + 1]);
+        MG_LAUNCH(P.C.n, lat_restrict_kernel, P, k, b, rhs[l + 1], L->constrained, c->mg[l + 1]->constrained);
+    }
+    // ---------------- upward
+    for (int l = nl - 2; l >= 1; --l) {
+        MGLevel* L = c->mg[l];
+        Lat lat = make_lat(L->d, L->m);
+        LatPair P = make_pair(L, c->mg[l + 1]);
+        double* a = xcur[l];
+        double* b = (a == bufA[l]) ? bufB[l] : bufA[l];
+        MG_LAUNCH(lat.n, lat_prolong_kernel, P, k, a, xcur[l + 1], L->constrained);
+        for (int s = 0; s < nu; ++s) {
+            MG_LAUNCH2(lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+            std::swap(a, b);
+        }
+        xcur[l] = a;
+    }
+    MG_LAUNCH(n, fine_prolong_kernel, n, lat1, L0->d, k, cur, ldc, xcur[1], L0->cidx, L0->frac, L0->constrained);
+    for (int s = 0; s < nu; ++s) {
+        int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
+        if (rc) return rc;
+        swap0();
+    }
+    if (cur != Z) return sfem_fail(c, SFEM_ERR_STATE, "mg_apply: internal buffer parity error");
+    return SFEM_OK;
+}

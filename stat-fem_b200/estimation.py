@@ -1,0 +1,39 @@
+"""MAP / maximum-likelihood estimation of the model-discrepancy hyperparameters (API of estimation.py)."""
+import numpy as np
+from scipy.optimize import minimize
+from .parallel import COMM_SELF, comm_world
+from .LinearSolver import LinearSolver
+
+_SOLVER_KWARGS = ("P", "solver_parameters", "nullspace", "transpose_nullspace", "near_nullspace", "options_prefix")
+
+
+def estimate_params_MAP(A, b, G, data, priors=[None, None, None], start=None, ensemble_comm=COMM_SELF, **kwargs):
+    """Minimise the negative log posterior with L-BFGS-B from ``start`` (random in [-2.5, 2.5)^3 if omitted) and return
+    the LinearSolver with ``params`` set to the optimum (estimation.py:7-110).  Solver keywords go to LinearSolver,
+    everything else becomes SciPy ``options`` (estimation.py:65-76).  The three-parameter quasi-Newton driver stays on
+    the host; each evaluation is one fused GPU pass that returns value and gradient together."""
+    ls_kwargs = {k: v for k, v in kwargs.items() if k in _SOLVER_KWARGS}
+    minimize_kwargs = {k: v for k, v in kwargs.items() if k not in _SOLVER_KWARGS}
+    ls = LinearSolver(A, b, G, data, priors=priors, ensemble_comm=ensemble_comm, **ls_kwargs)
+    ls.solve_prior()
+    world = comm_world()
+    if start is None:
+        start = 5. * (np.random.random(3) - 0.5) if world.rank == 0 else None
+        start = world.bcast(start, root=0)
+    else:
+        assert np.array(start).shape == (3,), "bad shape for starting point"
+    ls.fuse_gradient = True
+    try:
+        fmin_dict = minimize(ls.logposterior, start, method='L-BFGS-B', jac=ls.logpost_deriv, options=minimize_kwargs)
+    finally:
+        ls.fuse_gradient = False
+    assert fmin_dict['success'], "minimization routine failed"
+    result = fmin_dict['x']
+    root_result = world.bcast(result, root=0)
+    same_result = np.allclose(root_result, result)
+    diff_arg = world.allreduce(int(not same_result))
+    assert not diff_arg, "minimization did not produce identical results across all processes"
+    world.barrier()
+    ls.set_params(root_result)
+    ls.minimize_result = fmin_dict
+    return ls

@@ -379,6 +379,11 @@ def assemble_stiffness(V, bcs=None, chunk=2_000_000):
     data = np.zeros(S.nnz)
     data[np.searchsorted(keyS, keyA)] = A.data
     A = sp.csr_matrix((data, S.indices, S.indptr), shape=(n, n))
+    # exact symmetry (element sums arrive in different orders for (i,j) and (j,i)); the pattern is symmetric
+    At = sp.csr_matrix((np.arange(1, S.nnz + 1, dtype=np.float64), S.indices, S.indptr), shape=(n, n)).T.tocsr()
+    At.sort_indices()
+    perm = At.data.astype(np.int64) - 1
+    A = sp.csr_matrix((0.5 * (data + data[perm]), S.indices, S.indptr), shape=(n, n))
     A.sort_indices()
     if bcs is not None:
         bc_list = bcs if isinstance(bcs, (list, tuple)) else [bcs]

@@ -1,0 +1,110 @@
+"""Ensemble (observation-column) parallelism: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference splits the sensor columns over a Firedrake ``Ensemble.ensemble_comm`` with PETSc's contiguous ownership
+rule and gathers the rows of the result on ensemble rank 0 (solving_utils.py:117-123, 146-159).  ``EnsembleComm`` is
+the equivalent object here; with no process group it degenerates to a single rank."""
+import numpy as np
+
+
+def ownership_range(n, rank, size):
+    "PETSc's default contiguous split of range(n): the first n % size ranks own one extra entry"
+    base, extra = divmod(int(n), int(size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class EnsembleComm(object):
+    """Communicator over which the independent FEM solves are divided (mpi4py-like surface used by the reference:
+    rank, size, bcast, barrier, allreduce)."""
+
+    def __init__(self, group=None, use_dist=None):
+        self._dist = None
+        self.group = group
+        if use_dist is None:
+            try:
+                import torch.distributed as dist
+                use_dist = dist.is_available() and dist.is_initialized()
+            except Exception:
+                use_dist = False
+        if use_dist:
+            import torch.distributed as dist
+            self._dist = dist
+            self.rank = dist.get_rank(group)
+            self.size = dist.get_world_size(group)
+        else:
+            self.rank, self.size = 0, 1
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+    def column_range(self, n):
+        return ownership_range(n, self.rank, self.size)
+
+    def bcast(self, obj, root=0):
+        if self._dist is None or self.size == 1:
+            return obj
+        box = [obj]
+        self._dist.broadcast_object_list(box, src=root, group=self.group)
+        return box[0]
+
+    def barrier(self):
+        if self._dist is not None and self.size > 1:
+            self._dist.barrier(group=self.group)
+
+    def allreduce(self, x, op=None):
+        if self._dist is None or self.size == 1:
+            return x
+        import torch
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64)).clone()
+        backend = self._dist.get_backend(self.group)
+        if backend == "nccl":
+            t = t.cuda()
+        self._dist.all_reduce(t, group=self.group)
+        out = t.cpu().numpy()
+        return out.item() if out.ndim == 0 else out
+
+    # ---- tensor collectives used by the sharded Cu assembly -------------------------------------------------
+    def all_gather_rows(self, local, counts):
+        """local: tensor (m x n_loc).  Returns a list of tensors (m x counts[s]) -- every rank's column block of the
+        same row range.  One collective per call; callers chunk over rows so the receive buffers stay small."""
+        if self._dist is None or self.size == 1:
+            return [local]
+        import torch
+        outs = [torch.empty((local.shape[0], int(cnt)), dtype=local.dtype, device=local.device) for cnt in counts]
+        self._dist.all_gather(outs, local.contiguous(), group=self.group)
+        return outs
+
+    def gather_rows_to_root(self, local, counts, root=0):
+        """local: tensor (counts[rank] x m) of result rows; returns the (sum(counts) x m) concatenation on root, None
+        elsewhere (the Scatter.toZero of solving_utils.py:152-155)."""
+        if self._dist is None or self.size == 1:
+            return local
+        import torch
+        if self.rank == root:
+            outs = [torch.empty((int(cnt), local.shape[1]), dtype=local.dtype, device=local.device) for cnt in counts]
+        else:
+            outs = None
+        backend = self._dist.get_backend(self.group)
+        if backend == "nccl":
+            # NCCL gather: point-to-point sends to the root
+            if self.rank == root:
+                outs[root].copy_(local)
+                reqs = [self._dist.irecv(outs[s], src=s, group=self.group) for s in range(self.size) if s != root]
+                for r in reqs:
+                    r.wait()
+            else:
+                self._dist.send(local.contiguous(), dst=root, group=self.group)
+        else:
+            self._dist.gather(local.contiguous(), outs, dst=root, group=self.group)
+        return torch.cat(outs, dim=0) if self.rank == root else None
+
+
+COMM_SELF = EnsembleComm(use_dist=False)
+
+
+def comm_world():
+    "communicator over every launched process (the role of COMM_WORLD in LinearSolver.py:617, estimation.py:88-106)"
+    return EnsembleComm()

@@ -1,0 +1,271 @@
+"""The conditioning solves of stat-fem (API of solving_utils.py in the reference) on the GPU.
+
+``interp_covariance_to_data`` is the hot loop of the reference: for every sensor it performs two PETSc KSP solves and
+one sparse mat-vec, one sensor at a time (solving_utils.py:139-142).  Here all sensor columns owned by this rank are
+advanced together:  Z = A^-1 P  (block PCG, csrc/cg.cu + mg.cu, using A = A^T to halve the solves),  W = G Z
+(csrc/spmm.cu),  result = W^T Z_left  (FP64 tensor-core GEMM, csrc/dgemm.cu)."""
+import ctypes as C
+import warnings
+import numpy as np
+from . import _lib
+from . import fem
+from .parallel import EnsembleComm, COMM_SELF, ownership_range
+from .ForcingCovariance import ForcingCovariance
+from .InterpolationMatrix import InterpolationMatrix
+
+_KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_size", "mg_nu", "mg_omega",
+                      "mg_max_coarse", "workspace_gb"}
+
+
+def _lattice_nodes(coords):
+    "level-1 lattice: 2^p + 1 nodes per direction with a spacing between one and two mesh widths"
+    n, d = coords.shape
+    lo, hi = coords.min(axis=0), coords.max(axis=0)
+    ext = np.where(hi > lo, hi - lo, 1.)
+    geo = float(np.prod(ext) ** (1. / d))
+    per_side = float(n) ** (1. / d)
+    m1 = []
+    for k in range(d):
+        cells = max(per_side * ext[k] / geo - 1., 2.)
+        p = max(int(np.ceil(np.log2(cells) - 1.e-9)) - 1, 1)
+        m1.append(2 ** p + 1)
+    return lo, hi, m1
+
+
+class SparseSolver(object):
+    """Stands where the reference has ``firedrake.LinearSolver(A, ...)`` (LinearSolver.py:136-140): owns the device
+    copy of the stiffness matrix and the multigrid hierarchy, and solves blocks of right-hand sides.
+
+    ``solver_parameters`` keys understood: ksp_rtol (default 1e-12), ksp_atol (0), ksp_max_it (500), pc_type ('mg' or
+    'jacobi'), block_size (columns advanced together), mg_nu, mg_omega.  Other PETSc keys (e.g. ``pc_type: lu``) are
+    ignored with a warning -- there is no direct-solver or CPU path."""
+
+    def __init__(self, A, P=None, solver_parameters=None, nullspace=None, transpose_nullspace=None,
+                 near_nullspace=None, options_prefix=None):
+        if not isinstance(A, fem.Matrix):
+            raise TypeError("A must be a firedrake matrix")
+        self.A = A
+        params = dict(solver_parameters or {})
+        for key in params:
+            if key not in _KNOWN_SOLVER_KEYS:
+                warnings.warn("solver parameter %r is not used by the GPU solver" % key)
+        pc = params.get("pc_type", "mg")
+        if pc not in ("mg", "jacobi"):
+            warnings.warn("pc_type %r is not available on the GPU; using the multigrid V-cycle" % pc)
+            pc = "mg"
+        self.precond = 1 if pc == "mg" else 0
+        self.rtol = float(params.get("ksp_rtol", 1.e-12))
+        self.atol = float(params.get("ksp_atol", 0.))
+        self.max_it = int(params.get("ksp_max_it", 500 if self.precond else 20000))
+        self.block_size = params.get("block_size", None)
+        self.workspace_gb = float(params.get("workspace_gb", 24.))
+        self.mg_nu = int(params.get("mg_nu", 2))
+        self.mg_omega = float(params.get("mg_omega", 0.8))
+        self.mg_max_coarse = int(params.get("mg_max_coarse", 600))
+        self.n = A.shape[0]
+        self.ctx = _lib.new_context()
+        self._work = None
+        self.last_iterations = 0
+        self.last_relres = np.zeros(0)
+        self.total_iterations = 0
+        ctx = self.ctx
+        self.dA = _lib.DeviceCSR(ctx, A.shape, A.indptr, A.indices, A.data)
+        ctx.check(_lib.lib().sfem_set_stiffness(ctx.handle, self.n, _lib.ptr(self.dA.indptr), _lib.ptr(self.dA.indices),
+                                                _lib.ptr(self.dA.data)))
+        self.bc_nodes = A.bc_nodes()
+        if self.precond == 1:
+            self._setup_multigrid()
+
+    def _setup_multigrid(self):
+        ctx, lib = self.ctx, _lib.lib()
+        coords = np.ascontiguousarray(self.A.function_space.coords, dtype=np.float64)
+        n, d = coords.shape
+        lo, hi, m1 = _lattice_nodes(coords)
+        mask = np.zeros(n, dtype=np.uint8)
+        mask[self.bc_nodes] = 1
+        self._d_coords = ctx.to_device(coords, np.float64)
+        self._d_mask = ctx.to_device(mask, np.uint8)
+        lo3 = (C.c_double * 3)(*(list(lo) + [0.] * (3 - d)))
+        hi3 = (C.c_double * 3)(*(list(hi) + [0.] * (3 - d)))
+        while True:
+            m3 = (C.c_int * 3)(*(m1 + [1] * (3 - d)))
+            rc = lib.sfem_mg_setup(ctx.handle, d, _lib.ptr(self._d_coords), _lib.ptr(self._d_mask), lo3, hi3, m3,
+                                   self.mg_nu, self.mg_omega, self.mg_max_coarse)
+            if rc == _lib.SFEM_ERR_LIMIT and max(m1) > 3:
+                m1 = [max((m - 1) // 2 + 1, 3) for m in m1]     # mesh edges longer than a lattice cell: coarser lattice
+                continue
+            ctx.check(rc)
+            break
+        self.lattice = m1
+        self.mg_levels = [int(lib.sfem_mg_level_size(ctx.handle, l)) for l in range(lib.sfem_mg_num_levels(ctx.handle))]
+
+    def __del__(self):
+        try:
+            _lib.destroy_context(self.ctx)
+        except Exception:
+            pass
+
+    # ---- block solves -----------------------------------------------------------------------------------------
+    def pick_block_size(self, ncols):
+        if self.block_size is not None:
+            return max(1, min(int(self.block_size), ncols))
+        per_col = self.n * 8 * 7.
+        kb = int(self.workspace_gb * 1.e9 / per_col)
+        kb = max(8, min(kb, 512))
+        if kb >= 64:
+            kb -= kb % 64
+        return max(1, min(kb, ncols))
+
+    def _workspace(self, k):
+        need = _lib.lib().sfem_solve_workspace_bytes(self.ctx.handle, k, self.precond)
+        if self._work is None or self._work.numel() < need + 256:
+            self._work = None
+            self._work = self.ctx.workspace(need)
+        return self._work, need
+
+    def solve_block(self, B, X):
+        """X (n x k device block, any row stride) = A^-1 B.  Raises NotConvergedError on stagnation."""
+        k = int(B.shape[1])
+        work, need = self._workspace(k)
+        iters = C.c_int(0)
+        relres = (C.c_double * k)()
+        base = work.data_ptr()
+        off = (-base) % 256
+        ctx = self.ctx
+        ctx.check(_lib.lib().sfem_solve_block(ctx.handle, k, _lib.ptr(B), int(B.stride(0)), _lib.ptr(X), int(X.stride(0)),
+                                              self.precond, self.rtol, self.atol, self.max_it, C.byref(iters), relres,
+                                              C.c_void_p(base + off), int(work.numel() - off)))
+        self.last_iterations = iters.value
+        self.total_iterations += iters.value
+        self.last_relres = np.frombuffer(relres, dtype=np.float64).copy()
+        return X
+
+    def solve_columns(self, P_csc, col_begin, ncols, out):
+        "out (n x ncols device) = A^-1 P[:, col_begin:col_begin+ncols], advancing block_size columns at a time"
+        ctx = self.ctx
+        kb = self.pick_block_size(ncols)
+        rhs = ctx.empty((self.n, kb + (kb & 1)))
+        self.block_iterations = []
+        for j0 in range(0, ncols, kb):
+            k = min(kb, ncols - j0)
+            B = rhs[:, :k]
+            ctx.check(_lib.lib().sfem_scatter_columns(ctx.handle, self.n, _lib.ptr(P_csc.indptr), _lib.ptr(P_csc.indices),
+                                                      _lib.ptr(P_csc.data), col_begin + j0, k, _lib.ptr(B), int(B.stride(0))))
+            self.solve_block(B, out[:, j0:j0 + k])
+            self.block_iterations.append(self.last_iterations)
+        return out
+
+    def solve_vector(self, rhs_dev, apply_bcs):
+        "single right-hand side on the device (length n) -> new device vector"
+        ctx = self.ctx
+        B = rhs_dev.clone().reshape(-1, 1)
+        if apply_bcs and self.bc_nodes.size:
+            B[ctx.to_device(self.bc_nodes.astype(np.int64), np.int64), 0] = 0.
+        X = ctx.empty((self.n, 1))
+        self.solve_block(B, X)
+        return X.reshape(-1)
+
+    def solve(self, x, b):
+        """firedrake-style ``solver.solve(x, b)``: homogeneous Dirichlet lifting of the right-hand side iff ``A.bcs`` is
+        set -- the switch solving_utils.py:46-57 flips around the covariance solves."""
+        xf = x.function if isinstance(x, fem.Vector) else x
+        bf = b.function if isinstance(b, fem.Vector) else b
+        sol = self.solve_vector(self.ctx.to_device(bf.data, np.float64), apply_bcs=self.A.bcs is not None)
+        xf.data[:] = sol.cpu().numpy()
+
+
+def _aga_device(G, ls, rhs_dev):
+    "A^-1 G A^-1 rhs on device vectors, Dirichlet lifting off (solving_utils.py:46-57)"
+    x = ls.solve_vector(rhs_dev, apply_bcs=False)
+    w = G.G.matmul(x)
+    return ls.solve_vector(w, apply_bcs=False)
+
+
+def solve_forcing_covariance(G, ls, rhs):
+    "A^-1 G A^-1 rhs for one mesh-space vector (solving_utils.py:10-59)"
+    if not isinstance(G, ForcingCovariance):
+        raise TypeError("G must be a ForcingCovariance object")
+    if not isinstance(ls, SparseSolver):
+        raise TypeError("ls must be a firedrake LinearSolver")
+    if not isinstance(rhs, fem.Vector):
+        raise TypeError("rhs must be a firedrake vector")
+    if not G.is_assembled:
+        G.assemble()
+    out = _aga_device(G, ls, ls.ctx.to_device(rhs.array, np.float64))
+    f = fem.Function(G.function_space, out.cpu().numpy())
+    return f.vector()
+
+
+def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF, return_device=False):
+    """Phi_l^T A^-1 G A^-1 Phi_r on the root process, ``(0, 0)`` elsewhere (solving_utils.py:61-169).
+
+    Row i of the reference's temporary array is ``P_left^T (A^-1 G A^-1 p_i)`` and the flattened array is *reshaped*
+    to ``(n_left, n_right)``; with Z = A^-1 P and W = G Z_right that array is W^T Z_left.  The sensor columns of the
+    right matrix are split over ``ensemble_comm`` exactly as PETSc would (lines 117-123); each rank solves its columns,
+    all-gathers row-chunks of Z_left and accumulates its rows of W^T Z_left, which are then gathered on rank 0."""
+    if not isinstance(im_left, InterpolationMatrix):
+        raise TypeError("first argument to interp_covariance_to_data must be an InterpolationMatrix")
+    if not isinstance(ls, SparseSolver):
+        raise TypeError("ls must be a firedrake LinearSolver")
+    if not isinstance(G, ForcingCovariance):
+        raise TypeError("G must be a ForcingCovariance class")
+    if not isinstance(im_right, InterpolationMatrix):
+        raise TypeError("fourth argument to interp_covariance_to_data must be an InterpolationMatrix")
+    if not isinstance(ensemble_comm, EnsembleComm):
+        raise TypeError("ensemble_comm must be an MPI communicator created from a firedrake Ensemble")
+    for obj in (im_left, im_right, G):
+        if not obj.is_assembled:
+            obj.assemble()
+    ctx = ls.ctx
+    lib = _lib.lib()
+    n = ls.n
+    n_left, n_right = im_left.n_data, im_right.n_data
+    rank, size = ensemble_comm.rank, ensemble_comm.size
+    imin, imax = ensemble_comm.column_range(n_right)
+    nloc = imax - imin
+    same = (im_left is im_right) or (n_left == n_right and np.array_equal(im_left.coords, im_right.coords))
+
+    # Z_right (this rank's columns) and W = G Z_right
+    Zr = ctx.empty((n, max(nloc, 1)))[:, :nloc]
+    if nloc:
+        ls.solve_columns(im_right.csc, imin, nloc, Zr)
+    Wr = ctx.empty((n, max(nloc, 1)))[:, :nloc]
+    if nloc:
+        G.G.matmul(Zr, out=Wr)
+    # Z_left: this rank's share of the left columns
+    if same:
+        lmin, lmax, Zl = imin, imax, Zr
+    else:
+        lmin, lmax = ensemble_comm.column_range(n_left)
+        Zl = ctx.empty((n, max(lmax - lmin, 1)))[:, :lmax - lmin]
+        if lmax > lmin:
+            ls.solve_columns(im_left.csc, lmin, lmax - lmin, Zl)
+    # rows [imin, imax) of the (n_right x n_left) array  W^T Z_left
+    res = ctx.zeros((max(nloc, 1), n_left))[:nloc]
+    if size == 1:
+        if nloc and n_left:
+            ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, nloc, n_left, n, 1.0, _lib.ptr(Wr), int(Wr.stride(0)),
+                                     _lib.ptr(Zl), int(Zl.stride(0)), 0.0, _lib.ptr(res), int(res.stride(0))))
+    else:
+        lcounts = [ownership_range(n_left, s, size) for s in range(size)]
+        chunk = max(1024, min(n, int(2.e9 / (8. * max(n_left, 1)))))
+        for k0 in range(0, n, chunk):
+            k1 = min(n, k0 + chunk)
+            pieces = ensemble_comm.all_gather_rows(Zl[k0:k1, :], [b - a for a, b in lcounts])
+            for (a, b), piece in zip(lcounts, pieces):
+                if nloc and b > a:
+                    sub = res[:, a:b]
+                    ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, nloc, b - a, k1 - k0, 1.0,
+                                             _lib.ptr(Wr[k0:k1]), int(Wr.stride(0)), _lib.ptr(piece), int(piece.stride(0)),
+                                             1.0, _lib.ptr(sub), int(sub.stride(0))))
+    if size > 1:
+        rcounts = [ownership_range(n_right, s, size) for s in range(size)]
+        full = ensemble_comm.gather_rows_to_root(res.contiguous(), [b - a for a, b in rcounts])
+    else:
+        full = res
+    if im_left.comm.rank == 0 and rank == 0:
+        out = full.reshape(-1).reshape(n_left, n_right)      # the reference's reshape (lines 164-169)
+        return out if return_device else out.cpu().numpy()
+    if return_device:
+        return None
+    return np.zeros((0, 0))

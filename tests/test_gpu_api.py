@@ -1,0 +1,212 @@
+"""GPU parity tests of the drop-in API (ForcingCovariance / InterpolationMatrix / LinearSolver / solve_* /
+estimate_params_MAP) against the golden outputs of the unmodified reference (tests/golden/*.npz) and the oracle.
+They mirror the reference's own tests (stat_fem/tests/test_*.py)."""
+import numpy as np
+import scipy.sparse as sp
+import pytest
+from numpy.testing import assert_allclose
+
+from conftest import load_case, relerr, CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.e-8       # north_star: posterior means and covariances within 1e-8 relative
+TOL_LP = 1.e-6    # logposterior, gradient and MAP parameters
+
+
+def build(c):
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    V = fem.P1Space(fem.Mesh(c["coords"], c["cells"]))
+    bc = fem.DirichletBC(V, 0., c["bc_nodes"])
+    A = fem.Matrix(V, c["A_indptr"], c["A_indices"], c["A_data"], [bc])
+    b = fem.Function(V, c["b"])
+    G = stat_fem.ForcingCovariance(V, float(c["sigma_f"]), float(c["l_f"]), float(c["cutoff"]), float(c["reg"]))
+    od = stat_fem.ObsData(c["sensors"], c["data"], c["unc"])
+    return stat_fem, fem, V, A, b, G, od
+
+
+@pytest.fixture(params=CASES)
+def case(request):
+    c = load_case(request.param)
+    c["name"] = request.param
+    return c
+
+
+def test_forcing_covariance_mult_and_str(case):
+    "test_ForcingCovariance.py:112-127: G.mult by ones"
+    stat_fem, fem, V, A, b, G, od = build(case)
+    x = fem.Function(V, np.ones(V.dim())).vector()
+    y = fem.Function(V).vector()
+    G.mult(x, y)
+    assert G.is_assembled
+    assert relerr(y.gather(), case["G_ones"]) < 1e-13
+    assert str(G) == "Forcing Covariance with {} mesh points".format(V.dim())
+    assert G.get_nx() == V.dim() and G.get_nx_local() == V.dim()
+    G.assemble()    # idempotent
+    assert stat_fem.assemble(G) is G
+    G.destroy()
+    assert not G.is_assembled
+
+
+def test_interpolation_matrix(case):
+    "test_InterpolationMatrix.py: entries, P d, P^T v, columns"
+    stat_fem, fem, V, A, b, G, od = build(case)
+    im = stat_fem.InterpolationMatrix(V, case["sensors"].reshape(len(case["sensors"]), -1))
+    im.assemble()
+    assert_allclose(im.interp.toarray(), case["P"], atol=1e-10)
+    rng = np.random.default_rng(0)
+    dvec = rng.normal(size=im.n_data)
+    assert_allclose(im.interp_data_to_mesh(dvec).gather(), case["P"] @ dvec, atol=1e-12)
+    v = fem.Function(V, rng.normal(size=V.dim())).vector()
+    assert_allclose(im.interp_mesh_to_data(v), case["P"].T @ v.gather(), atol=1e-12)
+    for idx in (0, im.n_data - 1):
+        assert_allclose(im.get_meshspace_column_vector(idx).gather(), case["P"][:, idx], atol=1e-10)
+    with pytest.raises(AssertionError):
+        im.get_meshspace_column_vector(im.n_data)
+    with pytest.raises(AssertionError):
+        im.interp_data_to_mesh(np.zeros(im.n_data + 1))
+    with pytest.raises(TypeError):
+        im.interp_mesh_to_data(np.zeros(V.dim()))
+    assert str(im) == "Interpolation matrix from {} mesh points to {} data points".format(V.dim(), im.n_data)
+    im.destroy()
+
+
+def test_solve_forcing_covariance(case):
+    "test_solving_utils.py:16-33"
+    stat_fem, fem, V, A, b, G, od = build(case)
+    from stat_fem_b200.solving_utils import SparseSolver, solve_forcing_covariance
+    ls = SparseSolver(A)
+    rhs = fem.Function(V, np.ones(V.dim())).vector()
+    out = solve_forcing_covariance(G, ls, rhs)
+    assert relerr(out.gather(), case["AGA_ones"]) < TOL
+    with pytest.raises(TypeError):
+        solve_forcing_covariance(G, ls, np.ones(V.dim()))
+    with pytest.raises(TypeError):
+        solve_forcing_covariance(G, A, rhs)
+
+
+def test_prior_posterior_against_reference(case):
+    c = case
+    stat_fem, fem, V, A, b, G, od = build(c)
+    ls = stat_fem.LinearSolver(A, b, G, od)
+    mu, Cu = ls.solve_prior()
+    assert relerr(mu, c["mu"]) < TOL
+    assert relerr(Cu, c["Cu"]) < TOL
+    assert relerr(ls.x.vector().gather(), c["x_prior"]) < TOL
+    mu2, Cu2 = stat_fem.solve_prior(A, b, G, od)
+    assert relerr(mu2, c["mu"]) < TOL and relerr(Cu2, c["Cu"]) < TOL
+
+    with pytest.raises(ValueError):
+        ls.solve_posterior(fem.Function(V))
+    ls.set_params(c["params"])
+    u = fem.Function(V)
+    ls.solve_posterior(u)
+    assert relerr(u.vector().gather(), c["post_mean"]) < TOL
+    us = fem.Function(V)
+    ls.solve_posterior(us, scale_mean=True)
+    assert relerr(us.vector().gather(), c["post_mean_scaled"]) < TOL
+    u2 = fem.Function(V)
+    stat_fem.solve_posterior(A, u2, b, G, od, c["params"])
+    assert relerr(u2.vector().gather(), c["post_mean"]) < TOL
+
+    muy, Cuy = ls.solve_posterior_covariance()
+    assert relerr(muy, c["muy"]) < TOL
+    assert relerr(Cuy, c["Cuy"]) < TOL
+    muys, _ = ls.solve_posterior_covariance(scale_mean=True)
+    assert relerr(muys, c["muy_scaled"]) < TOL
+    muy2, Cuy2 = stat_fem.solve_posterior_covariance(A, b, G, od, c["params"])
+    assert relerr(muy2, c["muy"]) < TOL and relerr(Cuy2, c["Cuy"]) < TOL
+
+    m_eta, C_eta = ls.solve_prior_generating()
+    assert relerr(m_eta, c["m_eta"]) < TOL and relerr(C_eta, c["C_eta"]) < TOL
+    if "m_etay" in c:
+        m_etay, C_etay = ls.solve_posterior_generating()
+        assert relerr(m_etay, c["m_etay"]) < TOL and relerr(C_etay, c["C_etay"]) < TOL
+        m2, C2 = stat_fem.solve_posterior_generating(A, b, G, od, c["params"])
+        assert relerr(m2, c["m_etay"]) < TOL and relerr(C2, c["C_etay"]) < TOL
+
+
+def test_logposterior_and_gradient(case):
+    c = case
+    stat_fem, fem, V, A, b, G, od = build(c)
+    ls = stat_fem.LinearSolver(A, b, G, od)
+    lp = ls.logposterior(c["params"])
+    assert abs(lp - float(c["logpost"])) <= TOL_LP * abs(float(c["logpost"]))
+    assert_allclose(ls.logpost_deriv(c["params"]), c["logpost_deriv"], rtol=TOL_LP, atol=TOL_LP * max(1., np.max(np.abs(c["logpost_deriv"]))))
+    for p, v, g in zip(c["lp_points"], c["lp_values"], c["lp_derivs"]):
+        assert abs(ls.logposterior(p) - v) <= TOL_LP * abs(v)
+        assert_allclose(ls.logpost_deriv(p), g, rtol=TOL_LP, atol=TOL_LP * max(1., np.max(np.abs(g))))
+    # forward finite differences, dx = 1e-8 (test_LinearSolver.py:366-383); values scale with the magnitude of logpost
+    if c["name"] == "ref1d":
+        p0 = c["params"]
+        fd = np.array([(ls.logposterior(p0 + 1e-8 * np.eye(3)[k]) - ls.logposterior(p0)) / 1e-8 for k in range(3)])
+        assert_allclose(ls.logpost_deriv(p0), fd, atol=1e-6, rtol=1e-6)
+
+
+def test_predict(case):
+    c = case
+    if "predict_coords" not in c:
+        pytest.skip("no prediction golden")
+    stat_fem, fem, V, A, b, G, od = build(c)
+    ls = stat_fem.LinearSolver(A, b, G, od)
+    ls.set_params(c["params"])
+    pc = c["predict_coords"]
+    assert relerr(ls.predict_mean(pc), c["predict_mean"]) < TOL
+    assert relerr(ls.predict_mean(pc, scale_mean=False), c["predict_mean_unscaled"]) < TOL
+    assert relerr(ls.predict_covariance(pc, 0.1), c["predict_cov"]) < TOL
+    assert relerr(stat_fem.predict_mean(A, b, G, od, c["params"], pc), c["predict_mean"]) < TOL
+    assert relerr(stat_fem.predict_covariance(A, b, G, od, c["params"], pc, 0.1), c["predict_cov"]) < TOL
+    with pytest.raises(AssertionError):
+        ls.predict_covariance(np.zeros((1, V.mesh().cell_dimension() + 1)), 0.1)
+
+
+def test_estimate_params_MAP(case):
+    c = case
+    if "map_params" not in c:
+        pytest.skip("no MAP golden")
+    stat_fem, fem, V, A, b, G, od = build(c)
+    kw = {}
+    if np.isfinite(c["map_kwargs_ftol"]):
+        kw = dict(ftol=float(c["map_kwargs_ftol"]), gtol=float(c["map_kwargs_gtol"]))
+    ls = stat_fem.estimate_params_MAP(A, b, G, od, start=c["map_start"], solver_parameters={"ksp_rtol": 1e-13}, **kw)
+    lp = ls.logposterior(ls.params)
+    print(c["name"], "theta* =", ls.params, "ref", c["map_params"], "f* =", lp, "ref", float(c["map_logpost"]),
+          "evals", ls.n_logpost_evals)
+    assert abs(lp - float(c["map_logpost"])) <= TOL_LP * max(1., abs(float(c["map_logpost"])))
+    if kw:     # tight tolerances: the optimum itself is pinned
+        assert_allclose(ls.params, c["map_params"], rtol=1e-4, atol=1e-4)
+    # seeded random start (test_estimation.py:27-35) runs and succeeds
+    np.random.seed(234)
+    ls2 = stat_fem.estimate_params_MAP(A, b, G, od)
+    assert ls2.params.shape == (3,)
+
+
+def test_cu_full_size_property():
+    """Size-independent property at a mesh the O(n^2) reference cannot reach in seconds: Cu = (G Z)^T Z equals the
+    oracle's per-column two-solve loop on a random subset of columns (257^2 nodes, 64 sensors)."""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    import oracle
+    nodes = 257
+    V, A, b = fem.poisson_problem(nodes, 2)
+    h = 1. / (nodes - 1)
+    sig, l = np.log(2.e-2), np.log(1.5 * h)
+    reg = 1.e-8 * h ** 4 * np.exp(2 * sig)
+    rng = np.random.default_rng(1)
+    s = rng.uniform(0.02, 0.98, (64, 2))
+    od = stat_fem.ObsData(s, np.zeros(64), 2.e-3)
+    G = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg)
+    ls = stat_fem.LinearSolver(A, b, G, od)
+    mu, Cu = ls.solve_prior()
+    ip, ix, v = G.G.to_host()
+    n = V.dim()
+    Gs = sp.csr_matrix((v, ix, ip), shape=(n, n))
+    P = oracle.build_interpolation_matrix(V.coords, V.mesh().cells, s[:64])
+    ols = oracle.OracleLinearSolver(A.to_scipy(), b.data, Gs, oracle.OracleObsData(s, np.zeros(64), 2.e-3), P, A.bc_nodes())
+    cols = (3, 40)
+    rows = oracle.interp_covariance_to_data(P, Gs, ols.solver, P, col_range=cols)
+    assert relerr(Cu[cols[0]:cols[1]], rows) < TOL
+    omu = P.T @ ols.solver.solve(b.data, bcs_on=True)
+    assert relerr(mu, omu) < TOL
+    print("257^2: CG iterations per block", ls.solver.block_iterations, "levels", ls.solver.mg_levels)
