@@ -18,7 +18,7 @@ _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_si
 
 
 def _lattice_nodes(coords):
-    "level-1 lattice: 2^p + 1 nodes per direction with a spacing between one and two mesh widths"
+    "level-1 lattice: 2^p + 1 nodes per direction with a spacing of 1.5 to 3 mesh widths"
     n, d = coords.shape
     lo, hi = coords.min(axis=0), coords.max(axis=0)
     ext = np.where(hi > lo, hi - lo, 1.)
@@ -27,7 +27,7 @@ def _lattice_nodes(coords):
     m1 = []
     for k in range(d):
         cells = max(per_side * ext[k] / geo - 1., 2.)
-        p = max(int(np.ceil(np.log2(cells) - 1.e-9)) - 1, 1)
+        p = max(int(np.floor(np.log2(cells / 1.5) + 1.e-9)), 1)      # lattice spacing in [1.5, 3) mesh widths
         m1.append(2 ** p + 1)
     return lo, hi, m1
 

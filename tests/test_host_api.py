@@ -177,7 +177,7 @@ def test_ownership_range_is_petsc_split():
 def test_lattice_choice():
     from stat_fem_b200.solving_utils import _lattice_nodes
     from stat_fem_b200 import fem
-    for nodes, expect in ((1024, 513), (1025, 513), (101, 65), (33, 17), (11, 9)):
+    for nodes, expect in ((1024, 513), (1025, 513), (130, 65), (101, 65), (33, 17), (11, 5)):
         xs = np.linspace(0, 1, nodes)
         lo, hi, m1 = _lattice_nodes(np.stack(np.meshgrid(xs, xs), -1).reshape(-1, 2)) if nodes < 200 else \
             _lattice_nodes(np.stack([np.tile(xs, nodes), np.repeat(xs, nodes)], 1))
