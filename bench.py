@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-posterior of stat-fem's data-conditioning hot path on B200.
+
+One *step* = one full pass of the hot path over one synthetic problem (BASELINE.json config 2 by default):
+    G assembly -> stiffness upload + multigrid setup -> Z = A^-1 P (n_obs columns) -> W = G Z -> Cu = W^T Z, mu
+    -> for each of the data snapshots: MAP estimate (L-BFGS-B, start 0) + posterior mean on the mesh.
+`value`  : seconds per step with every input already resident in HBM and no result copied back (device-timed).
+`e2e`    : seconds per step through the public drop-in API with HOST buffers (NumPy in, NumPy out).
+`roofline`: the CSR stiffness-operator kernel family (csr_block_kernel: q = A p, Jacobi sweep, residual), timed live
+            with CUDA events inside the timed region; algorithmic bytes per launch are documented in DESIGN.md.
+`--impl reference`: the NumPy/SciPy restatement of the reference (oracle/) on the box's host cores, bounded sample,
+            extrapolated linearly to the full workload (the faithful O(n^2) reference cannot run config 2 in full).
+
+Launch: python bench.py --gpus N --steps K --warmup W          (N > 1: under torch.distributed.run, one rank/GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dim, nodes per side, n_obs, snapshots, l_f factor)
+    "c2": (2, 1024, 4096, 8, 1.5),      # BASELINE.json configs[1]: 2-D Poisson 1024^2 P1, 4096 observations, 8 snapshots
+    "c1": (2, 101, 100, 1, 1.5),        # configs[0] geometry (101^2, 100 sensors) with the benchmark-style scaled nugget
+    "mid": (2, 513, 1024, 4, 1.5),
+    "tiny": (2, 65, 64, 2, 1.5),
+}
+MAP_EVALS_ASSUMED = 40     # evaluations per MAP assumed when extrapolating the CPU reference (measured on GPU: 30-60)
+
+
+def make_problem(name):
+    from stat_fem_b200 import fem
+    dim, nodes, nobs, nsnap, lfac = WORKLOADS[name]
+    V, A, b = fem.poisson_problem(nodes, dim)
+    h = 1. / (nodes - 1)
+    sigma_f = np.log(2.e-2)
+    l_f = np.log(lfac * h)
+    reg = 1.e-8 * h ** (2 * dim) * np.exp(2 * sigma_f)        # nugget scaled with (h^d)^2 e^{2 sigma}
+    sensors = np.random.default_rng(1).uniform(0.02, 0.98, (nobs, dim))
+    truth = 0.7 * np.prod(np.sin(2. * np.pi * sensors), axis=1)
+    datas = []
+    for s in range(nsnap):
+        rng = np.random.default_rng(100 + s)
+        disc = np.zeros(nobs)
+        for m in range(6):      # smooth low-rank discrepancy ~ O(1e-2)
+            kvec = rng.uniform(0.5, 2.5, dim)
+            disc += 4.e-3 * rng.normal() * np.sin(np.pi * sensors @ kvec + rng.uniform(0, 2 * np.pi))
+        datas.append(truth + disc + rng.normal(scale=2.e-3, size=nobs))
+    return dict(name=name, dim=dim, nodes=nodes, nobs=nobs, nsnap=nsnap, V=V, A=A, b=b, sigma_f=sigma_f, l_f=l_f,
+                reg=reg, cutoff=1.e-3, sensors=sensors, datas=datas, unc=2.e-3, h=h)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gpu_step(prob, comm, resident, stats=None):
+    """one pass of the hot path through the drop-in API; returns a small dict of results"""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    from stat_fem_b200.estimation import fit_linear_solver
+    V, A, b = prob["V"], prob["A"], prob["b"]
+    G = stat_fem.ForcingCovariance(V, prob["sigma_f"], prob["l_f"], prob["cutoff"], prob["reg"])
+    G.assemble()
+    ods = [stat_fem.ObsData(prob["sensors"], y, prob["unc"]) for y in prob["datas"]]
+    ls = stat_fem.LinearSolver(A, b, G, ods[0], ensemble_comm=comm)
+    if resident and "im" in prob:
+        ls.im = prob["im"]              # interpolation matrix already assembled and resident in HBM
+        ls._owns_im = False
+    ls.host_results = not resident
+    mu, Cu = ls.solve_prior()
+    out = dict(nnzG=G.G.nnz, iters=list(ls.solver.block_iterations), thetas=[], evals=0)
+    xs = []
+    for s, od in enumerate(ods):
+        lss = ls if s == 0 else ls.clone_for_data(od)
+        fit_linear_solver(lss, start=np.zeros(3))
+        out["thetas"].append(lss.params.copy())
+        out["evals"] += lss.n_logpost_evals
+        x = fem.Function(V)
+        lss.solve_posterior(x, scale_mean=True)
+        xs.append(x)
+    out["mu0"] = float(mu[0]) if len(mu) else 0.
+    out["x_norm"] = float(np.linalg.norm(xs[-1].data))
+    if stats is not None:
+        stats["profile"] = ls.solver.ctx.profile_read()
+    out["ls"], out["G"] = ls, G
+    return out
+
+
+def bytes_h2d(prob):
+    V, A = prob["V"], prob["A"]
+    n, d = V.coords.shape
+    by = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + V.coords.nbytes + 8 * n + 8 * n + n       # A, coords, int_basis, b, mask
+    by += prob["nobs"] * (d + 1) * 12 * 2 + prob["sensors"].nbytes + prob["nsnap"] * 8 * prob["nobs"]   # P (CSC + CSR), sensors, data
+    return int(by)
+
+
+def bytes_d2h(prob):
+    n = prob["V"].dim()
+    return int(8 * prob["nobs"] ** 2 + 8 * prob["nobs"] + 8 * n + prob["nsnap"] * 8 * n)   # Cu, mu, prior x, posterior means
+
+
+class ClockSampler(threading.Thread):
+    "nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import _lib, fem
+    comm = stat_fem.EnsembleComm() if world > 1 else stat_fem.COMM_SELF
+    prob = make_problem(args.workload)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    CSR_TAGS = ("csr_mult_A", "csr_jacobi_A", "csr_resid_A")
+    csr_mask = 0b111
+
+    def timed_steps(nsteps, resident):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events, max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.total_launches()
+        prof = {t: dict(ms=0., bytes=0., count=0) for t in CSR_TAGS}
+        res = None
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            stats = {}
+            hook = _ProfileHook(csr_mask)
+            with hook:
+                res = gpu_step(prob, comm, resident, stats)
+            for t in CSR_TAGS:
+                for key in ("ms", "bytes", "count"):
+                    prof[t][key] += stats["profile"][t][key]
+            res.pop("ls"); res.pop("G")
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) * 1e-3
+        tmax = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        launches = _lib.total_launches() - launches0
+        return float(tmax[0]), float(tmax[1]), launches, prof, res
+
+    # device-resident arm: inputs cached in HBM (uploaded during warm-up), outputs stay on the device
+    _lib.DEVICE_CACHE[0] = True
+    im = stat_fem.InterpolationMatrix(prob["V"], prob["sensors"])
+    im.assemble()
+    prob["im"] = im
+    for _ in range(args.warmup):
+        r = gpu_step(prob, comm, True, {})
+        r.pop("ls"); r.pop("G")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_s, wall_s, launches, prof, res = timed_steps(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else {}
+    # end-to-end arm: host buffers in, host arrays out, nothing cached
+    _lib.DEVICE_CACHE[0] = False
+    for obj in (prob["V"], prob["A"], prob["b"]):
+        obj.__dict__.pop("_dev_cache", None)
+    prob.pop("im")
+    e2e_steps = max(1, min(args.steps, 2))
+    r = gpu_step(prob, comm, False, {})
+    r.pop("ls"); r.pop("G")
+    _, e2e_wall, _, _, _ = timed_steps(e2e_steps, False)
+
+    # per-family breakdown of one more (untimed) resident step, for profiles/ and the log
+    _lib.DEVICE_CACHE[0] = True
+    hook = _ProfileHook(0xffffffff)
+    stats = {}
+    with hook:
+        r = gpu_step(prob, comm, True, stats)
+    full_prof = stats["profile"]
+    gprof = r["G"].G.ctx.profile_read()
+    r.pop("ls"); r.pop("G")
+    _lib.DEVICE_CACHE[0] = False
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    csr_ms = sum(prof[t]["ms"] for t in CSR_TAGS)
+    csr_bytes = sum(prof[t]["bytes"] for t in CSR_TAGS)
+    csr_count = sum(prof[t]["count"] for t in CSR_TAGS)
+    achieved = csr_bytes / (csr_ms * 1e-3) / 1e9 if csr_ms > 0 else 0.
+    line = {
+        "metric": "time-to-posterior (s)", "value": dev_s / args.steps, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %dD Poisson, %d^%d P1 nodes (%d DOF), %d observations, %d snapshots, G cutoff 1e-3 "
+                               "(%.1f nnz/row); step = G assembly + MG setup + %d-column PCG solve + W=GZ + Cu=W^T Z + mean + "
+                               "%d x (MAP + posterior mean)" % (prob["name"], prob["dim"], prob["nodes"], prob["dim"], prob["V"].dim(),
+                                                                 prob["nobs"], prob["nsnap"], res["nnzG"] / prob["V"].dim(),
+                                                                 prob["nobs"], prob["nsnap"]),
+                   "parallelism": "observation columns sharded over %d GPU(s)" % world,
+                   "l2": "working set (>= %.1f GB per vector block) exceeds the 126 MB L2; no flush needed" %
+                         (8e-9 * prob["V"].dim() * min(prob["nobs"], 384)),
+                   "cg_iterations_per_block": res["iters"], "map_evaluations": res["evals"]},
+        "e2e": {"value": e2e_wall / e2e_steps, "unit": "s", "h2d_bytes_per_step": bytes_h2d(prob),
+                "d2h_bytes_per_step": bytes_d2h(prob), "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "csr_block_kernel (stiffness operator: q=Ap+dot, Jacobi sweep, residual)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": _read_traffic(), "launches": int(csr_count), "avg_launch_ms": csr_ms / max(csr_count, 1),
+                     "peak_source": peak_src},
+        "phases_ms": {k: round(v["ms"], 3) for k, v in full_prof.items() if v["count"]},
+        "phases_gcov_ms": {k: round(v["ms"], 3) for k, v in gprof.items() if v["count"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(prob, budget="small")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _ProfileHook(object):
+    """turn the library's per-family event timers on for every context created inside the block"""
+
+    def __init__(self, mask):
+        self.mask = mask
+
+    def __enter__(self):
+        from stat_fem_b200 import _lib
+        self._orig = _lib.Context.__init__
+        mask = self.mask
+        orig = self._orig
+
+        def init(ctx_self, device=None):
+            orig(ctx_self, device)
+            ctx_self.profile_enable(mask)
+        _lib.Context.__init__ = init
+        for c in _lib._live:
+            if c.handle:
+                c.profile_enable(mask)
+        return self
+
+    def __exit__(self, *a):
+        from stat_fem_b200 import _lib
+        _lib.Context.__init__ = self._orig
+        return False
+
+
+def _read_traffic():
+    "DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any"
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["csr_block_kernel_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+_G = {}
+
+
+def _g_row_worker(i):
+    import oracle
+    p = _G["p"]
+    d, _ = oracle.compute_G_rows(p["coords"], p["b"], p["sigma_f"], p["l_f"], p["cutoff"], p["reg"], rows=[i])
+    return len(d[i][1])
+
+
+def _solve_worker(j):
+    import oracle
+    col = np.asarray(_G["P"][:, j].todense()).ravel()
+    x = oracle.solve_forcing_covariance(_G["Gs"], _G["solver"], col)     # 2 solves + 1 SpMV, solving_utils.py:49-53
+    return _G["PT"] @ x
+
+
+def cpu_reference(prob, budget="small"):
+    """The reference algorithm (oracle/: NumPy/SciPy restatement pinned against the unmodified reference) on the host
+    cores, bounded sample, extrapolated linearly to the full workload.  Returns the cpu_baseline dict."""
+    import multiprocessing as mp
+    import scipy.sparse as sp
+    import oracle
+    from oracle.solver import _DirectSolver
+    cores = len(os.sched_getaffinity(0))
+    V, A = prob["V"], prob["A"]
+    n, nobs, nsnap = V.dim(), prob["nobs"], prob["nsnap"]
+    g_rows, cols, pairs = {"small": (8 * cores, 2 * cores, 1), "full": (32 * cores, 4 * cores, 2)}[budget]
+    g_rows, cols = min(g_rows, n), min(cols, nobs)
+    rng = np.random.default_rng(0)
+    _G["p"] = dict(coords=V.coords, b=V.integrate_basis_functions(), sigma_f=prob["sigma_f"], l_f=prob["l_f"],
+                   cutoff=prob["cutoff"], reg=prob["reg"])
+    ctxmp = mp.get_context("fork")
+    rows = rng.choice(n, g_rows, replace=False)
+    with ctxmp.Pool(cores) as pool:
+        pool.map(_g_row_worker, [int(i) for i in rows[:cores]])       # start the workers before the clock
+        t = time.perf_counter()
+        pool.map(_g_row_worker, [int(i) for i in rows])
+        t_g = (time.perf_counter() - t) / g_rows * n                  # O(n^2) row loop, ForcingCovariance.py:159-167
+    # G for the solves: the fast (cKDTree) oracle variant builds the same matrix; not timed as reference work
+    t = time.perf_counter()
+    ip, ix, v = oracle.compute_G_csr_fast(V.coords, _G["p"]["b"], prob["sigma_f"], prob["l_f"], prob["cutoff"], prob["reg"],
+                                          rows=rows[: max(8, g_rows // 4)])
+    t_g_fast = (time.perf_counter() - t) / max(8, g_rows // 4) * n
+    # banded stand-in with the same nnz/row is enough for timing the SpMV inside solve_forcing_covariance
+    nnz_row = max(1, int(round(len(ix) / max(8, g_rows // 4))))
+    offs = np.arange(-(nnz_row // 2), nnz_row - nnz_row // 2)
+    _G["Gs"] = sp.diags([np.full(n - abs(o), 1e-12) for o in offs], offs, shape=(n, n), format="csr")
+    t = time.perf_counter()
+    _G["solver"] = _DirectSolver(A.to_scipy(), A.bc_nodes())
+    t_factor = time.perf_counter() - t
+    cells, w = V.mesh().locate_cells(prob["sensors"][:cols])
+    nodes = V.mesh().cells[cells]
+    _G["P"] = sp.csc_matrix((w.ravel(), (nodes.ravel(), np.repeat(np.arange(cols), nodes.shape[1]))), shape=(n, cols))
+    _G["PT"] = _G["P"].T.tocsr()
+    with ctxmp.Pool(min(cores, cols)) as pool:
+        pool.map(_solve_worker, list(range(min(cores, cols))))
+        t = time.perf_counter()
+        pool.map(_solve_worker, list(range(cols)))
+        t_cols = (time.perf_counter() - t) / cols * nobs              # 2 n_obs solves, solving_utils.py:139-142
+    t_mean = t_cols / nobs * (0.5 + 2. * nsnap)                       # mean solve + 2 x (2 solves) per posterior mean
+    # dense end: one logposterior + one logpost_deriv in the reference's formulation (LinearSolver.py:592-691)
+    sens = prob["sensors"]
+    od = oracle.OracleObsData(sens, prob["datas"][0], prob["unc"])
+    X = rng.normal(size=(nobs, 64))
+    Cu = 1e-6 * (X @ X.T) / 64
+    ols = oracle.OracleLinearSolver.__new__(oracle.OracleLinearSolver)
+    ols.data, ols.Cu, ols.mu, ols.params = od, Cu, np.zeros(nobs), None
+    th = np.array([np.log(0.7), np.log(1e-2), np.log(0.5)])
+    t = time.perf_counter()
+    for _ in range(pairs):
+        ols.logposterior(th)
+        ols.logpost_deriv(th)
+    t_pair = (time.perf_counter() - t) / pairs
+    t_map = t_pair * MAP_EVALS_ASSUMED * nsnap
+    total = t_g + t_factor + t_cols + t_mean + t_map
+    return {"value": total, "unit": "s", "cores": cores, "kind": "port",
+            "sample": "%d of %d G rows (O(n^2) reference loop), LU factor in full, %d of %d sensor columns (2 solves + SpMV "
+                      "each), %d logposterior+logpost_deriv pair(s) at n_obs=%d; extrapolated linearly, MAP assumed %d "
+                      "evaluations x %d snapshots" % (g_rows, n, cols, nobs, pairs, nobs, MAP_EVALS_ASSUMED, nsnap),
+            "parts_s": {"G_assembly_reference_On2": t_g, "G_assembly_kdtree_variant": t_g_fast, "lu_factor": t_factor,
+                        "cu_solves": t_cols, "mean_and_posterior_solves": t_mean, "map": t_map}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob = make_problem(args.workload)
+    for _ in range(min(args.warmup, 1)):
+        small = dict(prob)
+        cpu_reference(small, budget="small")
+    vals = []
+    last = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_reference(prob, budget="small")
+        vals.append(last["value"])
+    val = float(np.mean(vals))
+    last["value"] = val
+    line = {"impl": "reference", "metric": "time-to-posterior (s)", "value": val, "unit": "s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %dD Poisson %d^%d nodes, %d observations, %d snapshots (CPU: extrapolated from a bounded sample)"
+                                   % (prob["name"], prob["dim"], prob["nodes"], prob["dim"], prob["nobs"], prob["nsnap"])},
+            "cpu_baseline": last, "gpu_launches": 0,
+            "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,15 @@ int sfem_destroy(sfem_ctx* ctx);
 const char* sfem_last_error(sfem_ctx* ctx);
 long long sfem_launch_count(sfem_ctx* ctx);   /* kernels launched so far by this context */
 
+/* ---- measurement: per-kernel-family device time (CUDA events on the launch stream) and algorithmic bytes / flops.
+ *      mask bit t enables family t; sfem_profile_read fills arrays of sfem_profile_num_tags() entries (totals since
+ *      the last sfem_profile_enable).  No reference counterpart (the reference has no timers). */
+int sfem_profile_enable(sfem_ctx* ctx, unsigned mask);
+int sfem_profile_num_tags(void);
+const char* sfem_profile_tag_name(int tag);
+int sfem_profile_read(sfem_ctx* ctx, double* ms_out_host, double* bytes_out_host, double* flops_out_host,
+                      long long* count_out_host);
+
 /* ---- stiffness matrix and the sparse solve (replaces firedrake LinearSolver/PETSc KSP: LinearSolver.py:136-140,
  *      solving_utils.py:49-53, LinearSolver.py:217) --------------------------------------------------------------- */
 /* A: n x n CSR, symmetric positive definite, Dirichlet rows AND columns replaced by identity (as Firedrake assembles
@@ -69,8 +78,8 @@ int sfem_solve_block(sfem_ctx* ctx, int k, const double* B, int64_t ldb, double*
 
 /* ---- generic CSR SpMM on multi-RHS blocks: Y (nrows x k) = S X.  Used for P d (InterpolationMatrix.py:213-221), P^T v
  *      (InterpolationMatrix.py:254-259, with P's CSC arrays read as the CSR of P^T) and G x (ForcingCovariance.py:242). */
-int sfem_spmm_csr(sfem_ctx* ctx, int64_t nrows, const int64_t* indptr, const int32_t* indices, const double* vals, int k,
-                  const double* X, int64_t ldx, double* Y, int64_t ldy);
+int sfem_spmm_csr(sfem_ctx* ctx, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                  const double* vals, int k, const double* X, int64_t ldx, double* Y, int64_t ldy);
 /* B (n x k, ldb) = dense copy of columns [col_begin, col_begin+k) of the CSC matrix P
  * (InterpolationMatrix.get_meshspace_column_vector, InterpolationMatrix.py:261-287, for a whole block of sensors). */
 int sfem_scatter_columns(sfem_ctx* ctx, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,

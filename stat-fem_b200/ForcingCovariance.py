@@ -85,8 +85,8 @@ class ForcingCovariance(object):
             cell_edge = R
             if R > 0. and float((hi - lo).max()) / R >= 4000.:
                 raise ValueError("cutoff radius is too small relative to the domain for the cell list")
-        d_coords = ctx.to_device(coords, np.float64)
-        d_b = ctx.to_device(int_basis, np.float64)
+        d_coords = _lib.cached_upload(self.function_space, "coords", ctx, lambda: ctx.to_device(coords, np.float64))
+        d_b = _lib.cached_upload(self.function_space, "int_basis", ctx, lambda: ctx.to_device(int_basis, np.float64))
         import torch
         d_indptr = ctx.empty((n + 1,), torch.int64)
         d_border = ctx.empty((_BORDER_CAP,), torch.int32)

@@ -56,10 +56,29 @@ class LinearSolver(object):
         self._cache = None
         self.fuse_gradient = False      # set by estimate_params_MAP: evaluate value and gradient in one pass
         self.n_logpost_evals = 0
+        self.host_results = True        # False: leave Cu on the device in solve_prior (bench.py's device-resident arm)
+
+    def clone_for_data(self, data):
+        """A LinearSolver for another data set at the SAME sensor locations that shares this one's stiffness solver,
+        interpolation matrix and cached prior (x, mu, Cu).  Extension over the reference, whose caches are per object
+        (LinearSolver.py:150-153): several data snapshots on one sensor array need the n_obs solves only once."""
+        if not isinstance(data, ObsData):
+            raise TypeError("data must be an ObsData type")
+        assert np.array_equal(data.get_coords(), self.data.get_coords()), "snapshots must share the sensor locations"
+        other = object.__new__(LinearSolver)
+        other.__dict__.update(self.__dict__)
+        other.data = data
+        other._owns_im = False
+        other.params = None
+        other._cache = None
+        other._dense_work = self._dense_work
+        other.n_logpost_evals = 0
+        return other
 
     def __del__(self):
         try:
-            self.im.destroy()
+            if self.__dict__.get("_owns_im", True):
+                self.im.destroy()
         except Exception:
             pass
 
@@ -90,16 +109,17 @@ class LinearSolver(object):
         self.x = fem.Function(self.G.function_space)
         if self.ensemble_comm.rank == 0:
             bf = self.b.function if isinstance(self.b, fem.Vector) else self.b
-            self._x_dev = self.solver.solve_vector(ctx.to_device(bf.data, np.float64),
+            self._x_dev = self.solver.solve_vector(_lib.cached_upload(bf, "data", ctx, lambda: ctx.to_device(bf.data, np.float64)),
                                                    apply_bcs=self.solver.A.bcs is not None)
-            self.x.data[:] = self._x_dev.cpu().numpy()
+            if self.host_results:
+                self.x.data[:] = self._x_dev.cpu().numpy()
             self._mu_dev = self.im.csc.matmul(self._x_dev)
             self.mu = self._mu_dev.cpu().numpy()
         else:
             self.mu = np.zeros(0)
         if Cu_dev is not None:
             self._Cu_dev = Cu_dev.contiguous()
-            self.Cu = self._Cu_dev.cpu().numpy()
+            self.Cu = self._Cu_dev.cpu().numpy() if self.host_results else self._Cu_dev
         else:
             self.Cu = np.zeros((0, 0))
         self._cache = None

@@ -21,7 +21,8 @@ EXPORTS = [
     "sfem_solve_workspace_bytes", "sfem_solve_block", "sfem_spmm_csr", "sfem_scatter_columns",
     "sfem_gcov_count", "sfem_gcov_fill", "sfem_dgemm", "sfem_potrf_dinv_doubles", "sfem_potrf", "sfem_potrs",
     "sfem_potri", "sfem_logdet", "sfem_kernel_matrix", "sfem_dense_workspace_bytes", "sfem_logpost",
-    "sfem_posterior_cov", "sfem_dense_solve", "sfem_cov_matrix", "sfem_axpby",
+    "sfem_posterior_cov", "sfem_dense_solve", "sfem_cov_matrix", "sfem_axpby", "sfem_profile_enable", "sfem_profile_num_tags",
+    "sfem_profile_tag_name", "sfem_profile_read",
 ]
 
 
@@ -47,7 +48,11 @@ def load_library():
         "sfem_mg_level_size": (i64, [vp, i32]),
         "sfem_solve_workspace_bytes": (sz, [vp, i32, i32]),
         "sfem_solve_block": (i32, [vp, i32, vp, i64, vp, i64, i32, f64, f64, i32, C.POINTER(i32), C.POINTER(f64), vp, sz]),
-        "sfem_spmm_csr": (i32, [vp, i64, vp, vp, vp, i32, vp, i64, vp, i64]),
+        "sfem_spmm_csr": (i32, [vp, i64, i64, vp, vp, vp, i32, vp, i64, vp, i64]),
+        "sfem_profile_enable": (i32, [vp, C.c_uint]),
+        "sfem_profile_num_tags": (i32, []),
+        "sfem_profile_tag_name": (C.c_char_p, [i32]),
+        "sfem_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_longlong)]),
         "sfem_scatter_columns": (i32, [vp, i64, vp, vp, vp, i64, i32, vp, i64]),
         "sfem_gcov_count": (i32, [vp, i64, i32, vp, vp, f64, f64, f64, f64, f64, f64, C.POINTER(f64), C.POINTER(f64), vp,
                                   C.POINTER(i64), C.POINTER(i64), vp, i32, C.POINTER(i64)]),
@@ -75,6 +80,9 @@ def load_library():
 
 _lib = None
 _ctx = {}
+_retired_launches = [0]
+_live = []
+DEVICE_CACHE = [False]     # bench.py's device-resident arm: keep uploaded inputs (A, coords, b, P) in HBM between steps
 
 
 def lib():
@@ -104,6 +112,7 @@ class Context(object):
         if rc != 0:
             raise RuntimeError("sfem_create failed (rc=%d): %s" % (rc, lib().sfem_last_error(None).decode()))
         self._keep = {}
+        _live.append(self)
 
     def check(self, rc):
         if rc == 0:
@@ -119,6 +128,18 @@ class Context(object):
 
     def launch_count(self):
         return int(lib().sfem_launch_count(self.handle))
+
+    def profile_enable(self, mask=0xffffffff):
+        self.check(lib().sfem_profile_enable(self.handle, mask))
+
+    def profile_read(self):
+        "dict tag-name -> dict(ms, bytes, flops, count) accumulated since profile_enable"
+        nt = lib().sfem_profile_num_tags()
+        ms, by, fl = (C.c_double * nt)(), (C.c_double * nt)(), (C.c_double * nt)()
+        cnt = (C.c_longlong * nt)()
+        self.check(lib().sfem_profile_read(self.handle, ms, by, fl, cnt))
+        return {lib().sfem_profile_tag_name(t).decode(): dict(ms=ms[t], bytes=by[t], flops=fl[t], count=int(cnt[t]))
+                for t in range(nt)}
 
     # ---- device memory helpers ------------------------------------------------------------------------
     def to_device(self, arr, dtype):
@@ -182,7 +203,7 @@ class DeviceCSR(object):
         k = int(X2.shape[1])
         Y = out if out is not None else ctx.empty((self.shape[0], k))
         Y2 = Y.reshape(-1, 1) if Y.dim() == 1 else Y
-        ctx.check(lib().sfem_spmm_csr(ctx.handle, self.shape[0], ptr(self.indptr), ptr(self.indices), ptr(self.data), k,
+        ctx.check(lib().sfem_spmm_csr(ctx.handle, self.shape[0], self.nnz, ptr(self.indptr), ptr(self.indices), ptr(self.data), k,
                                       ptr(X2), int(X2.stride(0)), ptr(Y2), int(Y2.stride(0))))
         return Y.reshape(-1) if vec and out is None else Y
 
@@ -197,5 +218,24 @@ def new_context(device=None):
 
 def destroy_context(ctx):
     if ctx is not None and ctx.handle:
+        _retired_launches[0] += ctx.launch_count()
         lib().sfem_destroy(ctx.handle)
         ctx.handle = C.c_void_p()
+        if ctx in _live:
+            _live.remove(ctx)
+
+
+def total_launches():
+    "kernels launched by this library in this process (all contexts, live or destroyed)"
+    return _retired_launches[0] + sum(c.launch_count() for c in _live if c.handle)
+
+
+def cached_upload(holder, key, ctx, build):
+    """device copy of a host input; kept on ``holder`` only while DEVICE_CACHE is on"""
+    if not DEVICE_CACHE[0]:
+        return build()
+    cache = holder.__dict__.setdefault("_dev_cache", {})
+    k = (key, ctx.device)
+    if k not in cache:
+        cache[k] = build()
+    return cache[k]

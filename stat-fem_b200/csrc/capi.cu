@@ -13,6 +13,9 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
 int scatter_columns(sfem_ctx* c, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,
                     int64_t col_begin, int k, double* B, int64_t ldb);
 void gcov_free(sfem_ctx* c);
+void prof_free(sfem_ctx* c);
+void prof_collect(sfem_ctx* c);
+void prof_reset(sfem_ctx* c);
 int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double* int_basis, double exp_2sigma,
                double exp_m2l, double cutoff, double reg, double bmax, double cell_edge, const double* lo,
                const double* hi, int64_t* indptr_out, int64_t* nnz_out, int64_t* max_row_nnz_out,
@@ -73,6 +76,7 @@ int sfem_destroy(sfem_ctx* c) {
     cudaStreamSynchronize(c->stream);
     mg_free(c);
     gcov_free(c);
+    prof_free(c);
     if (c->A_dinv) cudaFree(c->A_dinv);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -88,6 +92,10 @@ int sfem_set_stiffness(sfem_ctx* c, int64_t n, const int64_t* indptr, const int3
     if (n <= 0 || !indptr || !indices || !vals) return sfem_fail(c, SFEM_ERR_ARG, "set_stiffness: bad arguments");
     mg_free(c);
     c->n = n; c->A_ptr = indptr; c->A_idx = indices; c->A_val = vals;
+    int64_t nnz = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->A_nnz = nnz;
     return stiffness_dinv(c);
 }
 
@@ -106,10 +114,35 @@ int sfem_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X
     return cg_solve_block(c, k, B, ldb, X, ldx, precond, rtol, atol, max_it, iters_out_host, relres_out_host, work, work_bytes);
 }
 
-int sfem_spmm_csr(sfem_ctx* c, int64_t nrows, const int64_t* indptr, const int32_t* indices, const double* vals, int k,
-                  const double* X, int64_t ldx, double* Y, int64_t ldy) {
+int sfem_spmm_csr(sfem_ctx* c, int64_t nrows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const double* vals,
+                  int k, const double* X, int64_t ldx, double* Y, int64_t ldy) {
     GUARD(c);
-    return spmm_csr(c, nrows, indptr, indices, vals, k, X, ldx, Y, ldy, nullptr, nullptr);
+    return spmm_csr(c, TAG_SPMM_OTHER, nnz, nrows, indptr, indices, vals, k, X, ldx, Y, ldy, nullptr, nullptr);
+}
+
+int sfem_profile_enable(sfem_ctx* c, unsigned mask) {
+    GUARD(c);
+    prof_reset(c);
+    c->prof_mask = mask;
+    return SFEM_OK;
+}
+int sfem_profile_num_tags(void) { return TAG_COUNT; }
+const char* sfem_profile_tag_name(int tag) {
+    static const char* names[TAG_COUNT] = {"csr_mult_A", "csr_jacobi_A", "csr_resid_A", "spmm_other", "cg_vector",
+                                           "mg_transfer_fine", "mg_lattice", "dgemm", "potrf_panel", "gcov_count",
+                                           "gcov_fill", "dense_misc", "setup"};
+    return (tag >= 0 && tag < TAG_COUNT) ? names[tag] : "?";
+}
+int sfem_profile_read(sfem_ctx* c, double* ms_out_host, double* bytes_out_host, double* flops_out_host, long long* count_out_host) {
+    GUARD(c);
+    prof_collect(c);
+    for (int t = 0; t < TAG_COUNT; ++t) {
+        if (ms_out_host) ms_out_host[t] = c->prof_ms[t];
+        if (bytes_out_host) bytes_out_host[t] = c->prof_bytes[t];
+        if (flops_out_host) flops_out_host[t] = c->prof_flops[t];
+        if (count_out_host) count_out_host[t] = c->prof_count[t];
+    }
+    return SFEM_OK;
 }
 
 int sfem_scatter_columns(sfem_ctx* c, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,

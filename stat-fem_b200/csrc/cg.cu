@@ -259,14 +259,16 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     const bool jac = (precond == 0);
     int* h_nact = (int*)c->pinned;
 
-#define LAUNCH_V(kern, ...)                                                            \
+#define LAUNCH_V(passes, kern, ...)                                                    \
     do {                                                                               \
+        ProfScope _ps(c, TAG_CG_VEC, (passes) * 8.0 * (double)n * k, 0.0);             \
         if (v2) kern<2> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);              \
         else kern<1> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);                 \
         KCHECK(c);                                                                     \
     } while (0)
-#define LAUNCH_VJ(kern, ...)                                                           \
+#define LAUNCH_VJ(passes, kern, ...)                                                   \
     do {                                                                               \
+        ProfScope _ps(c, TAG_CG_VEC, (passes) * 8.0 * (double)n * k, 0.0);             \
         if (v2) { if (jac) kern<2, true> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);   \
                   else kern<2, false> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__); }    \
         else { if (jac) kern<1, true> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);      \
@@ -275,13 +277,13 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     } while (0)
 
     CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
-    LAUNCH_VJ(cg_init_kernel, n, k, B, ldb, X, ldx, R, P, c->A_dinv, part0, part1, g.rows_per_block);
+    LAUNCH_VJ(jac ? 4 : 3, cg_init_kernel, n, k, B, ldb, X, ldx, R, P, c->A_dinv, part0, part1, g.rows_per_block);
     cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, jac ? part1 : nullptr, s, rtol, atol);
     KCHECK(c);
     if (!jac) {
         int rc = mg_apply(c, k, R, k, Z, k, Q, mgwork);
         if (rc) return rc;
-        LAUNCH_V(cg_pz_kernel, n, k, R, Z, P, nullptr, part1, g.rows_per_block);
+        LAUNCH_V(3, cg_pz_kernel, n, k, R, Z, P, nullptr, part1, g.rows_per_block);
         cg_rho_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part1, s);
         KCHECK(c);
     }
@@ -290,21 +292,21 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     int it = 0;
     int nact = *h_nact;
     while (nact > 0 && it < max_it) {
-        int rc = spmm_csr(c, n, c->A_ptr, c->A_idx, c->A_val, k, P, k, Q, k, part0, nullptr);
+        int rc = spmm_csr(c, TAG_CSR_MULT, c->A_nnz, n, c->A_ptr, c->A_idx, c->A_val, k, P, k, Q, k, part0, nullptr);
         if (rc) return rc;
         cg_alpha_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s);
         KCHECK(c);
-        LAUNCH_VJ(cg_update_kernel, n, k, s.alpha, P, Q, X, ldx, R, c->A_dinv, part1, part2, g.rows_per_block);
+        LAUNCH_VJ(6, cg_update_kernel, n, k, s.alpha, P, Q, X, ldx, R, c->A_dinv, part1, part2, g.rows_per_block);
         if (!jac) {
             rc = mg_apply(c, k, R, k, Z, k, Q, mgwork);
             if (rc) return rc;
-            LAUNCH_V(cg_pz_kernel, n, k, R, Z, (double*)nullptr, nullptr, part2, g.rows_per_block);
+            LAUNCH_V(2, cg_pz_kernel, n, k, R, Z, (double*)nullptr, nullptr, part2, g.rows_per_block);
         }
         CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
         cg_beta_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part1, part2, s);
         KCHECK(c);
         CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LAUNCH_VJ(cg_pupdate_kernel, n, k, s.beta, jac ? R : Z, c->A_dinv, P, g.rows_per_block);
+        LAUNCH_VJ(3, cg_pupdate_kernel, n, k, s.beta, jac ? R : Z, c->A_dinv, P, g.rows_per_block);
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         nact = *h_nact;
         ++it;
@@ -314,7 +316,7 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     {
         int rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, X, ldx, R, k, B, ldb);
         if (rc) return rc;
-        LAUNCH_V(cg_norm_kernel, n, k, R, part0, g.rows_per_block);
+        LAUNCH_V(1, cg_norm_kernel, n, k, R, part0, g.rows_per_block);
         cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, relres_dev);
         KCHECK(c);
         if (relres_out_host) {

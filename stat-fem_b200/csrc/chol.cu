@@ -107,8 +107,11 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
         int nb = imin(NB, n - j0);
         double* Ajj = A + (int64_t)j0 * lda + j0;
         double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
-        potrf_panel_kernel<<<1, 256, dyn, c->stream>>>(Ajj, lda, nb, j0, Dj, info_dev);
-        KCHECK(c);
+        {
+            ProfScope ps(c, TAG_POTRF_PANEL, 24.0 * nb * nb, (2.0 / 3.0) * nb * nb * nb);
+            potrf_panel_kernel<<<1, 256, dyn, c->stream>>>(Ajj, lda, nb, j0, Dj, info_dev);
+            KCHECK(c);
+        }
         int m = n - j0 - nb;
         if (m > 0) {
             double* A21 = A + (int64_t)(j0 + nb) * lda + j0;

@@ -45,12 +45,23 @@ struct sfem_ctx {
         int* cell_start = nullptr;   // ncell+1
         int* cell_nodes = nullptr;   // n, ascending node index inside each cell
         int64_t max_row_nnz = 0;
+        int64_t nnz = 0;
     } gc;
 
     // ---- multigrid hierarchy (owned) -------------------------------------------------------------------
     std::vector<MGLevel*> mg;
     int mg_nu_pre = 2, mg_nu_post = 2;
     double mg_omega = 0.8;
+
+    // ---- optional per-kernel-family timing (CUDA events on the launch stream) + algorithmic work counters ------
+    unsigned prof_mask = 0;
+    struct ProfPair { int tag; cudaEvent_t e0, e1; };
+    std::vector<ProfPair> prof_pairs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[32] = {0};
+    double prof_bytes[32] = {0};
+    double prof_flops[32] = {0};
+    long long prof_count[32] = {0};
 
     // ---- scratch arena (owned, grows) --------------------------------------------------------------------
     void* scratch = nullptr; size_t scratch_bytes = 0;
@@ -77,6 +88,48 @@ void* sfem_scratch(sfem_ctx* c, size_t bytes);   // returns device scratch of at
                              cudaGetErrorString(_e));                                             \
     } while (0)
 
+// kernel families (tags) for sfem_profile_*
+enum {
+    TAG_CSR_MULT = 0,     // csr_block_kernel MODE_MULT / MODE_MULT_DOT on the stiffness matrix (q = A p, p^T q)
+    TAG_CSR_JACOBI = 1,   // csr_block_kernel MODE_JACOBI (fine-level smoother)
+    TAG_CSR_RESID = 2,    // csr_block_kernel MODE_RESID
+    TAG_SPMM_OTHER = 3,   // csr_block_kernel MODE_MULT on G / P / P^T
+    TAG_CG_VEC = 4,       // cg_init / cg_update / cg_pupdate / cg_pz / cg_norm
+    TAG_MG_XFER = 5,      // fine <-> lattice restriction / prolongation, jacobi0 on the fine level
+    TAG_MG_LATTICE = 6,   // everything on lattice levels
+    TAG_DGEMM = 7,
+    TAG_POTRF_PANEL = 8,
+    TAG_GCOV_COUNT = 9,
+    TAG_GCOV_FILL = 10,
+    TAG_DENSE_MISC = 11,  // kernel matrix, gradient reductions, small vector kernels
+    TAG_SETUP = 12,       // multigrid setup, cell lists, scans
+    TAG_COUNT = 13
+};
+
+struct ProfScope {
+    sfem_ctx* c;
+    int tag;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool on;
+    ProfScope(sfem_ctx* ctx, int t, double bytes, double flops) : c(ctx), tag(t) {
+        on = (c->prof_mask >> t) & 1u;
+        if (!on) return;
+        c->prof_bytes[t] += bytes;
+        c->prof_flops[t] += flops;
+        c->prof_count[t] += 1;
+        for (cudaEvent_t* e : {&e0, &e1}) {
+            if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(e0, c->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(e1, c->stream);
+        c->prof_pairs.push_back({tag, e0, e1});
+    }
+};
+
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
@@ -85,7 +138,7 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 
 // ---- internal entry points shared between translation units -------------------------------------------------
 // spmm.cu
-int spmm_csr(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val,
+int spmm_csr(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val,
              int k, const double* X, int64_t ldx, double* Y, int64_t ldy,
              double* dot_partials /*nullable: [nblk][k] of sum_i X[i][c]*Y[i][c]*/, int* nblk_out);
 // dgemm.cu

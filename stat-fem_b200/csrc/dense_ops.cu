@@ -134,6 +134,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int build_matrix(sfem_ctx* c, int n, int d, const double* Xs, double sigma, double l, const double* unc, int unc_vec,
                  double rho2, const double* Cu, int which, double* M) {
+    ProfScope ps(c, TAG_DENSE_MISC, 8.0 * (double)n * n * (Cu ? 2.0 : 1.0), 0.0);
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
     kernel_matrix_kernel<<<grd, blk, 0, c->stream>>>(n, n, d, Xs, Xs, exp(2.0 * sigma), exp(-2.0 * l), unc, unc_vec, rho2,
                                                      Cu, n, which, M, n);
@@ -221,6 +222,7 @@ int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, 
         rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
         if (rc) return rc;
         int nblk = 4 * SFEM_NUM_SMS;
+        ProfScope ps(c, TAG_DENSE_MISC, 16.0 * (double)n * n, 0.0);
         grad_reduce_kernel<<<nblk, 256, 0, c->stream>>>(n, d, Xs, exp(2.0 * sigma), exp(-2.0 * l), alpha, w.Kinv, Cu, w.partials);
         KCHECK(c);
         grad_final_kernel<<<1, 32, 0, c->stream>>>(nblk, w.partials, w.small + 16);

@@ -346,9 +346,12 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
     int* counters = reinterpret_cast<int*>(sums + nsum);
     CUDA_TRY(c, cudaMemsetAsync(counters, 0, 2 * sizeof(int), c->stream));
     p = make_params(c);
-    gcov_count_kernel<<<(unsigned)cdiv64(n, GC_WARPS), GC_WARPS * 32, 0, c->stream>>>(p, row_nnz, counters, counters + 1,
-                                                                                   borderline_rows, borderline_cap);
-    KCHECK(c);
+    {
+        ProfScope ps(c, TAG_GCOV_COUNT, 8.0 * (double)n * (d + 2), 0.0);
+        gcov_count_kernel<<<(unsigned)cdiv64(n, GC_WARPS), GC_WARPS * 32, 0, c->stream>>>(p, row_nnz, counters, counters + 1,
+                                                                                       borderline_rows, borderline_cap);
+        KCHECK(c);
+    }
     rc = exclusive_scan<int64_t>(c, row_nnz, n, indptr_out, sums);
     if (rc) return rc;
     int hc[2];
@@ -356,6 +359,7 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
     CUDA_TRY(c, cudaMemcpyAsync(nnz_out, indptr_out + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     g.max_row_nnz = hc[0];
+    g.nnz = *nnz_out;
     if (max_row_nnz_out) *max_row_nnz_out = hc[0];
     if (n_borderline_out) *n_borderline_out = hc[1];
     if (hc[0] > GC_LONG_CAP && g.ncell > 1)
@@ -368,8 +372,12 @@ int gcov_fill(sfem_ctx* c, const int64_t* indptr, int32_t* indices_out, double* 
     if (!g.cell_start) return sfem_fail(c, SFEM_ERR_STATE, "gcov_fill: call gcov_count first");
     GcP p = make_params(c);
     int presorted = (g.ncell == 1) ? 1 : 0;   // single cell: candidates are visited in ascending DOF order
-    gcov_fill_kernel<<<(unsigned)cdiv64(g.n, GC_WARPS), GC_WARPS * 32, 0, c->stream>>>(p, indptr, indices_out, vals_out, presorted);
-    KCHECK(c);
+    {
+        // algorithmic bytes: 12 per stored entry + row pointers + coordinates and basis integrals
+        ProfScope ps(c, TAG_GCOV_FILL, 12.0 * (double)g.nnz + 8.0 * (double)(g.n + 1) + 8.0 * (double)g.n * (g.d + 1), 0.0);
+        gcov_fill_kernel<<<(unsigned)cdiv64(g.n, GC_WARPS), GC_WARPS * 32, 0, c->stream>>>(p, indptr, indices_out, vals_out, presorted);
+        KCHECK(c);
+    }
     if (!presorted && g.max_row_nnz > GC_CAP) {
         size_t dyn = (sizeof(double) + sizeof(int)) * 16384;
         cudaFuncSetAttribute(gcov_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -709,15 +709,17 @@ size_t mg_workspace_bytes(sfem_ctx* c, int k) {
 int mg_num_levels(sfem_ctx* c) { return (int)c->mg.size(); }
 int64_t mg_level_size(sfem_ctx* c, int l) { return (l >= 0 && l < (int)c->mg.size()) ? c->mg[l]->n : -1; }
 
-#define MG_LAUNCH(nrows, kern, ...)                                                                  \
+#define MG_LAUNCH(tag, bytes, nrows, kern, ...)                                                      \
     do {                                                                                             \
+        ProfScope _ps(c, tag, bytes, 0.0);                                                           \
         RowGrid _g = row_grid(nrows);                                                                \
         if (v2) kern<2> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
         else kern<1> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
         KCHECK(c);                                                                                   \
     } while (0)
-#define MG_LAUNCH2(nrows, kern, MODE, ...)                                                           \
+#define MG_LAUNCH2(tag, bytes, nrows, kern, MODE, ...)                                               \
     do {                                                                                             \
+        ProfScope _ps(c, tag, bytes, 0.0);                                                           \
         RowGrid _g = row_grid(nrows);                                                                \
         if (v2) kern<2, MODE> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
         else kern<1, MODE> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
@@ -749,7 +751,7 @@ int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_
     double* cur = tmp0; int64_t ldc = k;
     double* oth = Z; int64_t ldo = ldz;
     auto swap0 = [&]() { std::swap(cur, oth); std::swap(ldc, ldo); };
-    MG_LAUNCH(n, jacobi0_kernel, n, k, R, ldr, cur, ldc, L0->dinv, om);
+    MG_LAUNCH(TAG_MG_XFER, 16.0 * (double)n * k, n, jacobi0_kernel, n, k, R, ldr, cur, ldc, L0->dinv, om);
     for (int s = 1; s < nu; ++s) {
         int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
         if (rc) return rc;
@@ -760,30 +762,30 @@ int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_
         if (rc) return rc;
     }
     Lat lat1 = make_lat(c->mg[1]->d, c->mg[1]->m);
-    MG_LAUNCH(lat1.n, fine_restrict_kernel, lat1, L0->d, k, oth, ldo, rhs[1], L0->cell_start, L0->cell_nodes, L0->frac,
+    MG_LAUNCH(TAG_MG_XFER, 8.0 * (double)(n + lat1.n) * k, lat1.n, fine_restrict_kernel, lat1, L0->d, k, oth, ldo, rhs[1], L0->cell_start, L0->cell_nodes, L0->frac,
               L0->constrained, c->mg[1]->constrained);
     // ---------------- lattice levels, downward
     for (int l = 1; l < nl; ++l) {
         MGLevel* L = c->mg[l];
         Lat lat = make_lat(L->d, L->m);
         if (l == nl - 1 && L->dense_inv) {
-            MG_LAUNCH(lat.n, dense_apply_kernel, (int)lat.n, k, L->dense_inv, rhs[l], bufA[l]);
+            MG_LAUNCH(TAG_MG_LATTICE, 16.0 * (double)lat.n * k, lat.n, dense_apply_kernel, (int)lat.n, k, L->dense_inv, rhs[l], bufA[l]);
             xcur[l] = bufA[l];
             break;
         }
         double* a = bufA[l];
         double* b = bufB[l];
-        MG_LAUNCH(lat.n, jacobi0_kernel, lat.n, k, rhs[l], (int64_t)k, a, (int64_t)k, L->dinv, om);
+        MG_LAUNCH(TAG_MG_LATTICE, 16.0 * (double)lat.n * k, lat.n, jacobi0_kernel, lat.n, k, rhs[l], (int64_t)k, a, (int64_t)k, L->dinv, om);
         int sweeps = (l == nl - 1) ? 8 * nu : nu;    // no dense inverse available: smooth harder on the last level
         for (int s = 1; s < sweeps; ++s) {
-            MG_LAUNCH2(lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+            MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
             std::swap(a, b);
         }
         xcur[l] = a;
         if (l == nl - 1) break;
-        MG_LAUNCH2(lat.n, lat_block_kernel, LM_RESID, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+        MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_RESID, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
         LatPair P = make_pair(L, c->mg[l + 1]);
-        MG_LAUNCH(P.C.n, lat_restrict_kernel, P, k, b, rhs[l + 1], L->constrained, c->mg[l + 1]->constrained);
+        MG_LAUNCH(TAG_MG_LATTICE, 8.0 * (double)(P.F.n + P.C.n) * k, P.C.n, lat_restrict_kernel, P, k, b, rhs[l + 1], L->constrained, c->mg[l + 1]->constrained);
     }
     // ---------------- upward
     for (int l = nl - 2; l >= 1; --l) {
@@ -792,14 +794,14 @@ int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_
         LatPair P = make_pair(L, c->mg[l + 1]);
         double* a = xcur[l];
         double* b = (a == bufA[l]) ? bufB[l] : bufA[l];
-        MG_LAUNCH(lat.n, lat_prolong_kernel, P, k, a, xcur[l + 1], L->constrained);
+        MG_LAUNCH(TAG_MG_LATTICE, 8.0 * (double)(2 * P.F.n + P.C.n) * k, lat.n, lat_prolong_kernel, P, k, a, xcur[l + 1], L->constrained);
         for (int s = 0; s < nu; ++s) {
-            MG_LAUNCH2(lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
+            MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
             std::swap(a, b);
         }
         xcur[l] = a;
     }
-    MG_LAUNCH(n, fine_prolong_kernel, n, lat1, L0->d, k, cur, ldc, xcur[1], L0->cidx, L0->frac, L0->constrained);
+    MG_LAUNCH(TAG_MG_XFER, 8.0 * (double)(2 * n + lat1.n) * k, n, fine_prolong_kernel, n, lat1, L0->d, k, cur, ldc, xcur[1], L0->cidx, L0->frac, L0->constrained);
     for (int s = 0; s < nu; ++s) {
         int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
         if (rc) return rc;

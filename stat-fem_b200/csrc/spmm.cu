@@ -66,10 +66,14 @@ __global__ void scatter_columns_kernel(const int64_t* __restrict__ colptr, const
 }
 
 template <int MODE>
-int launch_mode(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
-                const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
+int launch_mode(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val,
+                int k, const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
                 const double* dinv, double omega, double* partials) {
     RowGrid g = row_grid(n);
+    // algorithmic traffic: the matrix once, each vector block once
+    double vecs = (MODE == MODE_JACOBI || MODE == MODE_RESID) ? 24.0 : 16.0;
+    ProfScope ps(c, tag, vecs * (double)n * k + 12.0 * (double)nnz + 8.0 * (double)(n + 1) + (MODE == MODE_JACOBI ? 8.0 * n : 0.0),
+                 2.0 * (double)nnz * k);
     bool v2 = can_vec2(k, ldx, ldy, X, Y) && (B == nullptr || can_vec2(k, ldb, ldb, B, B));
     if (v2) {
         dim3 grid(g.nblk, (k + 63) / 64);
@@ -86,28 +90,30 @@ int launch_mode(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, 
 
 }  // namespace
 
-int spmm_csr(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
+int spmm_csr(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
              const double* X, int64_t ldx, double* Y, int64_t ldy, double* dot_partials, int* nblk_out) {
     if (nblk_out) *nblk_out = row_grid(n).nblk;
     if (n <= 0 || k <= 0) return SFEM_OK;
     if (dot_partials)
-        return launch_mode<MODE_MULT_DOT>(c, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, dot_partials);
-    return launch_mode<MODE_MULT>(c, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, nullptr);
+        return launch_mode<MODE_MULT_DOT>(c, tag, nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, dot_partials);
+    return launch_mode<MODE_MULT>(c, tag, nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, nullptr);
 }
 
+// the two fine-level multigrid operators always act on the stiffness matrix held by the context
 int csr_jacobi(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
                const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
                const double* dinv, double omega) {
-    return launch_mode<MODE_JACOBI>(c, n, ptr, idx, val, k, X, ldx, Y, ldy, B, ldb, dinv, omega, nullptr);
+    return launch_mode<MODE_JACOBI>(c, TAG_CSR_JACOBI, c->A_nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, B, ldb, dinv, omega, nullptr);
 }
 
 int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
                  const double* X, int64_t ldx, double* R, int64_t ldr, const double* B, int64_t ldb) {
-    return launch_mode<MODE_RESID>(c, n, ptr, idx, val, k, X, ldx, R, ldr, B, ldb, nullptr, 0.0, nullptr);
+    return launch_mode<MODE_RESID>(c, TAG_CSR_RESID, c->A_nnz, n, ptr, idx, val, k, X, ldx, R, ldr, B, ldb, nullptr, 0.0, nullptr);
 }
 
 int scatter_columns(sfem_ctx* c, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,
                     int64_t col_begin, int k, double* B, int64_t ldb) {
+    ProfScope ps(c, TAG_CG_VEC, 8.0 * (double)n * k, 0.0);
     CUDA_TRY(c, cudaMemset2DAsync(B, (size_t)ldb * sizeof(double), 0, (size_t)k * sizeof(double), (size_t)n, c->stream));
     scatter_columns_kernel<<<(k + 127) / 128, 128, 0, c->stream>>>(colptr, rows, vals, col_begin, k, B, ldb);
     KCHECK(c);

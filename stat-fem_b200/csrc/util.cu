@@ -12,6 +12,29 @@ int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
+void prof_collect(sfem_ctx* c) {
+    if (c->prof_pairs.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->prof_pairs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) c->prof_ms[p.tag] += ms;
+        c->prof_pool.push_back(p.e0);
+        c->prof_pool.push_back(p.e1);
+    }
+    c->prof_pairs.clear();
+}
+
+void prof_reset(sfem_ctx* c) {
+    prof_collect(c);
+    for (int t = 0; t < 32; ++t) { c->prof_ms[t] = 0; c->prof_bytes[t] = 0; c->prof_flops[t] = 0; c->prof_count[t] = 0; }
+}
+
+void prof_free(sfem_ctx* c) {
+    prof_collect(c);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    c->prof_pool.clear();
+}
+
 void* sfem_scratch(sfem_ctx* c, size_t bytes) {
     if (bytes <= c->scratch_bytes && c->scratch) return c->scratch;
     if (c->scratch) {

@@ -16,6 +16,12 @@ def estimate_params_MAP(A, b, G, data, priors=[None, None, None], start=None, en
     minimize_kwargs = {k: v for k, v in kwargs.items() if k not in _SOLVER_KWARGS}
     ls = LinearSolver(A, b, G, data, priors=priors, ensemble_comm=ensemble_comm, **ls_kwargs)
     ls.solve_prior()
+    return fit_linear_solver(ls, start=start, **minimize_kwargs)
+
+
+def fit_linear_solver(ls, start=None, **minimize_kwargs):
+    """The optimisation half of estimate_params_MAP (estimation.py:83-110) on an existing LinearSolver whose prior is
+    already cached -- e.g. one obtained with ``LinearSolver.clone_for_data`` for a further data snapshot."""
     world = comm_world()
     if start is None:
         start = 5. * (np.random.random(3) - 0.5) if world.rank == 0 else None

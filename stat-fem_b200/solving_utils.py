@@ -69,7 +69,7 @@ class SparseSolver(object):
         self.last_relres = np.zeros(0)
         self.total_iterations = 0
         ctx = self.ctx
-        self.dA = _lib.DeviceCSR(ctx, A.shape, A.indptr, A.indices, A.data)
+        self.dA = _lib.cached_upload(A, "csr", ctx, lambda: _lib.DeviceCSR(ctx, A.shape, A.indptr, A.indices, A.data))
         ctx.check(_lib.lib().sfem_set_stiffness(ctx.handle, self.n, _lib.ptr(self.dA.indptr), _lib.ptr(self.dA.indices),
                                                 _lib.ptr(self.dA.data)))
         self.bc_nodes = A.bc_nodes()
@@ -83,8 +83,8 @@ class SparseSolver(object):
         lo, hi, m1 = _lattice_nodes(coords)
         mask = np.zeros(n, dtype=np.uint8)
         mask[self.bc_nodes] = 1
-        self._d_coords = ctx.to_device(coords, np.float64)
-        self._d_mask = ctx.to_device(mask, np.uint8)
+        self._d_coords = _lib.cached_upload(self.A.function_space, "coords", ctx, lambda: ctx.to_device(coords, np.float64))
+        self._d_mask = _lib.cached_upload(self.A, "bcmask", ctx, lambda: ctx.to_device(mask, np.uint8))
         lo3 = (C.c_double * 3)(*(list(lo) + [0.] * (3 - d)))
         hi3 = (C.c_double * 3)(*(list(hi) + [0.] * (3 - d)))
         while True:
