@@ -13,59 +13,73 @@ constexpr int LDS = NB + 1;
 
 // Factor the nb x nb (nb <= 128) lower block at A (row-major, lda) in place and write inv(L) to Dinv (ld = 128,
 // explicit zeros above the diagonal and outside nb).  info: 0, or 1-based global index of the first bad pivot.
+//
+// One CTA, the block lives in shared memory with an odd row stride (129) so that "thread = row" accesses are
+// conflict-free and column reads are broadcasts.  Two threads share a row and split the k-range by parity.
+// Phase 1: right-looking Cholesky, two barriers per column.  Phase 2: in-place inversion of the triangular factor,
+// columns from last to first:  X[i][j] = -(1/L[j][j]) * sum_{k=j+1..i} X[i][k] L[k][j].
 __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A, int64_t lda, int nb, int j0,
                                                           double* __restrict__ Dinv, int* __restrict__ info) {
-    extern __shared__ double s[];   // [NB][LDS]
+    extern __shared__ double s[];   // [NB][LDS] + column buffer [NB] + pivots [NB]
+    double* colbuf = s + NB * LDS;
     const int tid = threadIdx.x;
-    for (int t = tid; t < nb * nb; t += blockDim.x) {
-        int i = t / nb, j = t % nb;
-        s[i * LDS + j] = (j <= i) ? A[(int64_t)i * lda + j] : 0.0;
+    const int i = tid >> 1, h = tid & 1;
+    for (int t = tid; t < NB * NB; t += blockDim.x) {
+        int r = t >> 7, cidx = t & (NB - 1);
+        s[r * LDS + cidx] = (r < nb && cidx <= r) ? A[(int64_t)r * lda + cidx] : ((r == cidx) ? 1.0 : 0.0);
     }
     __syncthreads();
+    // ---- phase 1: Cholesky.  The square roots of the pivots go to pivs[] and are put on the diagonal at the end, so
+    // the unscaled s[j][j] every thread reads is never overwritten while a slower warp may still be reading it.
+    double* pivs = colbuf + NB;
     for (int j = 0; j < nb; ++j) {
-        if (tid == 0) {
-            double dg = s[j * LDS + j];
-            if (!(dg > 0.0)) {
-                if (*info == 0) *info = j0 + j + 1;
-                dg = 1.0;
-            }
-            s[j * LDS + j] = sqrt(dg);
+        __syncthreads();                       // trailing update of column j-1 complete everywhere
+        double dg = s[j * LDS + j];
+        if (!(dg > 0.0)) {
+            if (tid == 0 && *info == 0) *info = j0 + j + 1;
+            dg = 1.0;
         }
-        __syncthreads();
-        double inv = 1.0 / s[j * LDS + j];
-        for (int i = j + 1 + tid; i < nb; i += blockDim.x) s[i * LDS + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: rows i > j, columns j < k <= i
-        int m = nb - j - 1;
-        for (int t = tid; t < m * m; t += blockDim.x) {
-            int ii = t / m, kk = t % m;
-            if (kk <= ii) {
-                int i = j + 1 + ii, k = j + 1 + kk;
-                s[i * LDS + k] -= s[i * LDS + j] * s[k * LDS + j];
-            }
+        double piv = sqrt(dg);
+        double lij = (i > j) ? s[i * LDS + j] / piv : 0.0;
+        __syncwarp();                          // both threads of a row have read s[i][j] before it is rescaled
+        if (h == 0) {
+            if (i > j) s[i * LDS + j] = lij;
+            else if (i == j) pivs[j] = piv;
         }
-        __syncthreads();
+        __syncthreads();                       // scaled column j visible to all rows
+        if (i > j) {
+            double* row = s + i * LDS;
+            for (int k = j + 1 + h; k <= i; k += 2) row[k] -= lij * s[k * LDS + j];
+        }
     }
+    __syncthreads();
+    if (tid < nb) s[tid * LDS + tid] = pivs[tid];
+    __syncthreads();
     for (int t = tid; t < nb * nb; t += blockDim.x) {
-        int i = t / nb, j = t % nb;
-        if (j <= i) A[(int64_t)i * lda + j] = s[i * LDS + j];
-    }
-    // inverse of the triangular block: thread c owns column c of X = inv(L); X lives in global (coalesced over c)
-    for (int t = tid; t < NB * NB; t += blockDim.x) Dinv[t] = 0.0;
-    __syncthreads();
-    if (tid < nb) {
-        int c = tid;
-        Dinv[c * NB + c] = 1.0 / s[c * LDS + c];
+        int r = t / nb, cidx = t % nb;
+        if (cidx <= r) A[(int64_t)r * lda + cidx] = s[r * LDS + cidx];
     }
     __syncthreads();
-    for (int i = 1; i < nb; ++i) {
-        if (tid < i) {
-            int c = tid;
-            double acc = 0.0;
-            for (int k = c; k < i; ++k) acc += s[i * LDS + k] * Dinv[k * NB + c];
-            Dinv[i * NB + c] = -acc / s[i * LDS + i];
+    // ---- phase 2: X = inv(L) in place (rows/cols >= nb hold the identity, harmless)
+    for (int j = NB - 1; j >= 0; --j) {
+        if (tid < NB) colbuf[tid] = s[tid * LDS + j];      // old column j of L (entries k >= j)
+        __syncthreads();
+        double xjj = 1.0 / colbuf[j];
+        double acc = 0.0;
+        if (i > j) {
+            const double* row = s + i * LDS;
+            for (int k = j + 1 + h; k <= i; k += 2) acc += row[k] * colbuf[k];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (h == 0) {
+            if (i > j) s[i * LDS + j] = -acc * xjj;
+            else if (i == j) s[j * LDS + j] = xjj;
         }
         __syncthreads();
+    }
+    for (int t = tid; t < NB * NB; t += blockDim.x) {
+        int r = t >> 7, cidx = t & (NB - 1);
+        Dinv[t] = (r < nb && cidx <= r && cidx < nb) ? s[r * LDS + cidx] : 0.0;
     }
 }
 
@@ -101,7 +115,7 @@ __global__ void mirror_lower_kernel(int n, double* __restrict__ A, int64_t ld) {
 // dinv: device buffer of ceil(n/128) * 128*128 doubles.  info_dev: device int (zeroed here).
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
     CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
-    size_t dyn = sizeof(double) * NB * LDS;
+    size_t dyn = sizeof(double) * (NB * LDS + 2 * NB);
     cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     for (int j0 = 0; j0 < n; j0 += NB) {
         int nb = imin(NB, n - j0);

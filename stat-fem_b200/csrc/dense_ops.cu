@@ -71,6 +71,19 @@ __global__ void mat_axpy_kernel(int64_t tot, const double* __restrict__ A, doubl
     if (i < tot) C[i] = A[i] + s * B[i];
 }
 
+// y = M x for a row-major n x n matrix: one warp per row, fixed-order shuffle reduction
+__global__ void __launch_bounds__(256) gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ x,
+                                                  double* __restrict__ y) {
+    int lane = threadIdx.x & 31;
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const double* m = M + (int64_t)row * n;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s += m[j] * x[j];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+}
+
 // deterministic single-block dot products: out[q] = x_q . y_q
 struct DotJob { const double* x; const double* y; };
 __global__ void dots_kernel(int n, DotJob j0, DotJob j1, DotJob j2, double* __restrict__ out) {
@@ -208,19 +221,26 @@ int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, 
     if (rc) return rc;
     axpby_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 1.0, y, -rho, mu, r);
     KCHECK(c);
-    CUDA_TRY(c, cudaMemcpyAsync(alpha, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
     if (rc) return rc;
-    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, alpha, 1);
-    if (rc) return rc;
+    if (grad_host) {
+        // the gradient needs inv(KCu) anyway (traces): use it for alpha = inv(KCu) r as well
+        rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
+        if (rc) return rc;
+        ProfScope ps(c, TAG_DENSE_MISC, 8.0 * (double)n * n, 2.0 * (double)n * n);
+        gemv_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(n, w.Kinv, r, alpha);
+        KCHECK(c);
+    } else {
+        CUDA_TRY(c, cudaMemcpyAsync(alpha, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        rc = potrs_lower(c, n, w.M, n, w.dinv, 1, alpha, 1);
+        if (rc) return rc;
+    }
     rc = logdet_lower(c, n, w.M, n, w.small + 8);
     if (rc) return rc;
     DotJob j0{r, alpha}, j1{mu, alpha}, jn{nullptr, nullptr};
     dots_kernel<<<1, 256, 0, c->stream>>>(n, j0, j1, jn, w.small);
     KCHECK(c);
     if (grad_host) {
-        rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
-        if (rc) return rc;
         int nblk = 4 * SFEM_NUM_SMS;
         ProfScope ps(c, TAG_DENSE_MISC, 16.0 * (double)n * n, 0.0);
         grad_reduce_kernel<<<nblk, 256, 0, c->stream>>>(n, d, Xs, exp(2.0 * sigma), exp(-2.0 * l), alpha, w.Kinv, Cu, w.partials);
