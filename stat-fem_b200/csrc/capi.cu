@@ -79,6 +79,7 @@ int sfem_destroy(sfem_ctx* c) {
     prof_free(c);
     if (c->A_dinv) cudaFree(c->A_dinv);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->dense_tmp) cudaFree(c->dense_tmp);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
     return SFEM_OK;

@@ -9,77 +9,200 @@
 namespace {
 
 constexpr int NB = 128;
-constexpr int LDS = NB + 1;
 
 // Factor the nb x nb (nb <= 128) lower block at A (row-major, lda) in place and write inv(L) to Dinv (ld = 128,
 // explicit zeros above the diagonal and outside nb).  info: 0, or 1-based global index of the first bad pivot.
 //
-// One CTA, the block lives in shared memory with an odd row stride (129) so that "thread = row" accesses are
-// conflict-free and column reads are broadcasts.  Two threads share a row and split the k-range by parity.
-// Phase 1: right-looking Cholesky, two barriers per column.  Phase 2: in-place inversion of the triangular factor,
-// columns from last to first:  X[i][j] = -(1/L[j][j]) * sum_{k=j+1..i} X[i][k] L[k][j].
-__global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A, int64_t lda, int nb, int j0,
-                                                          double* __restrict__ Dinv, int* __restrict__ info) {
-    extern __shared__ double s[];   // [NB][LDS] + column buffer [NB] + pivots [NB]
-    double* colbuf = s + NB * LDS;
-    const int tid = threadIdx.x;
-    const int i = tid >> 1, h = tid & 1;
-    for (int t = tid; t < NB * NB; t += blockDim.x) {
+// One CTA of 8 warps; the block lives in shared memory with row stride 132 (= 4 mod 16 doubles, so the
+// (row = lane/4, k = lane%4) operand fragments of mma.m8n8k4.f64 hit 16 distinct 8-byte banks per half-warp).
+// Phase 1, four 32-wide block steps:
+//   (i)   warp 0 factorises the 32x32 diagonal block in REGISTERS (lane = row, column values exchanged by shuffles;
+//         one rsqrt per column is the only long-latency operation on the chain),
+//   (ii)  warp 0 inverts that triangular block (lane = column, forward substitution with broadcast reads) while
+//         warps 1-7 solve the rows below it (thread = row, same substitution),
+//   (iii) all warps apply the symmetric rank-32 update to the trailing lower triangle with DMMA 8x8x4 tiles.
+// Phase 2: inv(L) in place, by 32x32 blocks:  M_kj = L_kj inv(D_j)  (one sweep), then block columns right to left,
+// rows bottom to top:  X_ij = - sum_{k=j+1..i} X_ik M_kj  (DMMA), which only reads not-yet-overwritten blocks.
+constexpr int PLD = 132;       // row stride of the panel in shared memory
+constexpr int DLD = 36;        // row stride of the 32x32 inverse diagonal blocks
+constexpr int SB = 32;         // sub-block width
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict__ A, int64_t lda, int nb, int j0,
+                                                             double* __restrict__ Dinv, int* __restrict__ info) {
+    extern __shared__ __align__(16) double s[];    // [NB][PLD] | Dv[4][32][DLD] | rd[NB]
+    double* Dv = s + NB * PLD;
+    double* rd = Dv + 4 * SB * DLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int t = tid; t < NB * NB; t += 256) {
         int r = t >> 7, cidx = t & (NB - 1);
-        s[r * LDS + cidx] = (r < nb && cidx <= r) ? A[(int64_t)r * lda + cidx] : ((r == cidx) ? 1.0 : 0.0);
+        double v = (r == cidx) ? 1.0 : 0.0;
+        if (r < nb && cidx <= r) v = A[(int64_t)r * lda + cidx];
+        s[r * PLD + cidx] = v;
     }
     __syncthreads();
-    // ---- phase 1: Cholesky.  The square roots of the pivots go to pivs[] and are put on the diagonal at the end, so
-    // the unscaled s[j][j] every thread reads is never overwritten while a slower warp may still be reading it.
-    double* pivs = colbuf + NB;
-    for (int j = 0; j < nb; ++j) {
-        __syncthreads();                       // trailing update of column j-1 complete everywhere
-        double dg = s[j * LDS + j];
-        if (!(dg > 0.0)) {
-            if (tid == 0 && *info == 0) *info = j0 + j + 1;
-            dg = 1.0;
+
+    // ------------------------------------------------------------------ phase 1: Cholesky by 32-wide block steps
+    for (int jb = 0; jb < NB / SB; ++jb) {
+        const int c0 = jb * SB, c1 = c0 + SB;
+        double rinvs[SB];
+        if (warp == 0) {
+            double a[SB];
+            const double* rowp = s + (c0 + lane) * PLD + c0;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) a[k] = (k <= lane) ? rowp[k] : 0.0;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                double d = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(d > 0.0)) {
+                    if (lane == 0 && *info == 0) *info = j0 + c0 + j + 1;
+                    d = 1.0;
+                }
+                double rinv = rsqrt(d);
+                rinv = rinv * fma(-0.5 * d * rinv, rinv, 1.5);       // one Newton step: relative error ~1e-32 -> rounds like 1/sqrt
+                rinvs[j] = rinv;
+                double lij = a[j] * rinv;
+                if (lane == j) { lij = d * rinv; rd[c0 + j] = rinv; }
+                a[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < SB; ++k) {
+                    double lkj = __shfl_sync(0xffffffffu, lij, k);
+                    a[k] = fma(-lij, lkj, a[k]);
+                }
+            }
+            double* roww = s + (c0 + lane) * PLD + c0;
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                if (k <= lane) roww[k] = a[k];
         }
-        double piv = sqrt(dg);
-        double lij = (i > j) ? s[i * LDS + j] / piv : 0.0;
-        __syncwarp();                          // both threads of a row have read s[i][j] before it is rescaled
-        if (h == 0) {
-            if (i > j) s[i * LDS + j] = lij;
-            else if (i == j) pivs[j] = piv;
+        __syncthreads();
+        if (warp == 0) {
+            // (ii) inverse of the diagonal block: lane = column
+            double x[SB];
+            double* dv = Dv + jb * SB * DLD;
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                double acc0 = (i == lane) ? 1.0 : 0.0, acc1 = 0.0;
+                const double* lrow = s + (c0 + i) * PLD + c0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) {
+                    if (k & 1) acc1 = fma(-lrow[k], x[k], acc1);
+                    else acc0 = fma(-lrow[k], x[k], acc0);
+                }
+                x[i] = (acc0 + acc1) * rinvs[i];
+                dv[i * DLD + lane] = x[i];
+            }
+        } else {
+            // rows below the diagonal block: solve  x D^T = a  (thread = row)
+            int r = c1 + (tid - 32);
+            if (r < NB) {
+                double x[SB];
+                double* rowp = s + r * PLD + c0;
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    double acc0 = rowp[j], acc1 = 0.0;
+                    const double* lrow = s + (c0 + j) * PLD + c0;
+#pragma unroll
+                    for (int k = 0; k < j; ++k) {
+                        if (k & 1) acc1 = fma(-lrow[k], x[k], acc1);
+                        else acc0 = fma(-lrow[k], x[k], acc0);
+                    }
+                    x[j] = (acc0 + acc1) * rd[c0 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < SB; ++j) rowp[j] = x[j];
+            }
         }
-        __syncthreads();                       // scaled column j visible to all rows
-        if (i > j) {
-            double* row = s + i * LDS;
-            for (int k = j + 1 + h; k <= i; k += 2) row[k] -= lij * s[k * LDS + j];
+        __syncthreads();
+        // (iii) trailing update of the lower triangle, 8x8 tiles
+        const int mt = (NB - c1) / 8;
+        int cnt = 0;
+        for (int ti = 0; ti < mt; ++ti) {
+            for (int tj = 0; tj <= ti; ++tj, ++cnt) {
+                if ((cnt & 7) != warp) continue;
+                const double* ap = s + (c1 + 8 * ti + lr) * PLD + c0 + lk;
+                const double* bp = s + (c1 + 8 * tj + lr) * PLD + c0 + lk;
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < SB / 4; ++ks) dmma_8x8x4(acc0, acc1, ap[4 * ks], bp[4 * ks]);
+                double2* cp = reinterpret_cast<double2*>(s + (c1 + 8 * ti + lr) * PLD + c1 + 8 * tj + 2 * lk);
+                double2 cv = *cp;
+                cv.x -= acc0; cv.y -= acc1;
+                *cp = cv;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid < nb) s[tid * LDS + tid] = pivs[tid];
-    __syncthreads();
-    for (int t = tid; t < nb * nb; t += blockDim.x) {
+    for (int t = tid; t < nb * nb; t += 256) {
         int r = t / nb, cidx = t % nb;
-        if (cidx <= r) A[(int64_t)r * lda + cidx] = s[r * LDS + cidx];
+        if (cidx <= r) A[(int64_t)r * lda + cidx] = s[r * PLD + cidx];
     }
     __syncthreads();
-    // ---- phase 2: X = inv(L) in place (rows/cols >= nb hold the identity, harmless)
-    for (int j = NB - 1; j >= 0; --j) {
-        if (tid < NB) colbuf[tid] = s[tid * LDS + j];      // old column j of L (entries k >= j)
-        __syncthreads();
-        double xjj = 1.0 / colbuf[j];
-        double acc = 0.0;
-        if (i > j) {
-            const double* row = s + i * LDS;
-            for (int k = j + 1 + h; k <= i; k += 2) acc += row[k] * colbuf[k];
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (h == 0) {
-            if (i > j) s[i * LDS + j] = -acc * xjj;
-            else if (i == j) s[j * LDS + j] = xjj;
-        }
-        __syncthreads();
+
+    // ------------------------------------------------------------------ phase 2: inv(L) in place
+    // step A: M_kj = L_kj inv(D_j); each warp owns whole 8-row strips, so the update is safe in place
+    {
+        int strip = 0;
+        for (int kb = 1; kb < 4; ++kb)
+            for (int jb = 0; jb < kb; ++jb)
+                for (int ts = 0; ts < 4; ++ts, ++strip) {
+                    if ((strip & 7) != warp) continue;
+                    double* rowp = s + (SB * kb + 8 * ts + lr) * PLD + SB * jb;
+                    double af[8];
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) af[ks] = rowp[4 * ks + lk];
+                    const double* dv = Dv + jb * SB * DLD;
+                    double acc[4][2];
+#pragma unroll
+                    for (int tn = 0; tn < 4; ++tn) {
+                        acc[tn][0] = acc[tn][1] = 0.0;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) dmma_8x8x4(acc[tn][0], acc[tn][1], af[ks], dv[(4 * ks + lk) * DLD + 8 * tn + lr]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int tn = 0; tn < 4; ++tn)
+                        *reinterpret_cast<double2*>(rowp + 8 * tn + 2 * lk) = make_double2(acc[tn][0], acc[tn][1]);
+                }
     }
-    for (int t = tid; t < NB * NB; t += blockDim.x) {
+    // diagonal blocks <- inv(D_j)
+    for (int t = tid; t < 4 * SB * SB; t += 256) {
+        int jb = t >> 10, r = (t >> 5) & 31, cidx = t & 31;
+        s[(SB * jb + r) * PLD + SB * jb + cidx] = Dv[jb * SB * DLD + r * DLD + cidx];
+    }
+    __syncthreads();
+    // step B
+    {
+        const int tr = warp >> 1, tc0 = (warp & 1) * 2;
+        for (int jb = 2; jb >= 0; --jb)
+            for (int ib = 3; ib > jb; --ib) {
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                for (int kb = jb + 1; kb <= ib; ++kb) {
+                    const double* ap = s + (SB * ib + 8 * tr + lr) * PLD + SB * kb + lk;
+                    const double* bp = s + (SB * kb + lk) * PLD + SB * jb + 8 * tc0 + lr;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double av = ap[4 * ks];
+                        dmma_8x8x4(acc[0][0], acc[0][1], av, bp[4 * ks * PLD]);
+                        dmma_8x8x4(acc[1][0], acc[1][1], av, bp[4 * ks * PLD + 8]);
+                    }
+                }
+                __syncthreads();
+                double* cp = s + (SB * ib + 8 * tr + lr) * PLD + SB * jb + 8 * tc0 + 2 * lk;
+                *reinterpret_cast<double2*>(cp) = make_double2(-acc[0][0], -acc[0][1]);
+                *reinterpret_cast<double2*>(cp + 8) = make_double2(-acc[1][0], -acc[1][1]);
+                __syncthreads();
+            }
+    }
+    for (int t = tid; t < NB * NB; t += 256) {
         int r = t >> 7, cidx = t & (NB - 1);
-        Dinv[t] = (r < nb && cidx <= r && cidx < nb) ? s[r * LDS + cidx] : 0.0;
+        Dinv[t] = (r < nb && cidx <= r && cidx < nb) ? s[r * PLD + cidx] : 0.0;
     }
 }
 
@@ -112,11 +235,38 @@ __global__ void mirror_lower_kernel(int n, double* __restrict__ A, int64_t ld) {
 
 }  // namespace
 
+static void* dense_tmp(sfem_ctx* c, size_t bytes) {
+    if (bytes <= c->dense_tmp_bytes && c->dense_tmp) return c->dense_tmp;
+    if (c->dense_tmp) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->dense_tmp);
+        c->dense_tmp = nullptr;
+        c->dense_tmp_bytes = 0;
+    }
+    if (cudaMalloc(&c->dense_tmp, bytes + 4096) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    c->dense_tmp_bytes = bytes + 4096;
+    return c->dense_tmp;
+}
+
 // dinv: device buffer of ceil(n/128) * 128*128 doubles.  info_dev: device int (zeroed here).
+// Right-looking, 128-wide panels.  The panel solve writes to a temporary (so it may use small tiles and fill the
+// machine), the trailing update reads that temporary, and the copy back into A is off the critical path.
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
     CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
-    size_t dyn = sizeof(double) * (NB * LDS + 2 * NB);
-    cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    size_t dyn = sizeof(double) * (NB * PLD + 4 * SB * DLD + NB);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        attr_set = true;
+    }
+    double* T = nullptr;
+    if (n > NB) {
+        T = (double*)dense_tmp(c, sizeof(double) * (size_t)n * NB);
+        if (!T) return sfem_fail(c, SFEM_ERR_CUDA, "potrf: temporary allocation failed");
+    }
     for (int j0 = 0; j0 < n; j0 += NB) {
         int nb = imin(NB, n - j0);
         double* Ajj = A + (int64_t)j0 * lda + j0;
@@ -130,10 +280,12 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
         if (m > 0) {
             double* A21 = A + (int64_t)(j0 + nb) * lda + j0;
             double* A22 = A + (int64_t)(j0 + nb) * lda + (j0 + nb);
-            int rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, A21, lda, 0);   // A21 <- A21 inv(L)^T
+            int rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);   // T = A21 inv(L_jj)^T
             if (rc) return rc;
-            rc = dgemm(c, OP_N, OP_T, m, m, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, 1);     // SYRK, lower tiles
+            rc = dgemm(c, OP_N, OP_T, m, m, nb, -1.0, T, NB, T, NB, 1.0, A22, lda, 1);             // SYRK, lower tiles
             if (rc) return rc;
+            CUDA_TRY(c, cudaMemcpy2DAsync(A21, sizeof(double) * lda, T, sizeof(double) * NB, sizeof(double) * nb, m,
+                                          cudaMemcpyDeviceToDevice, c->stream));
         }
     }
     return SFEM_OK;
@@ -146,7 +298,7 @@ int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* 
         int nb = imin(NB, n - j0);
         const double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
         double* Bj = B + (int64_t)j0 * ldb;
-        int rc = dgemm(c, OP_N, OP_N, nb, k, nb, 1.0, Dj, NB, Bj, ldb, 0.0, Bj, ldb, 0);
+        int rc = dgemm(c, OP_N, OP_N, nb, k, nb, 1.0, Dj, NB, Bj, ldb, 0.0, Bj, ldb, 4);
         if (rc) return rc;
         int m = n - j0 - nb;
         if (m > 0) {
@@ -161,7 +313,7 @@ int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* 
         int nb = imin(NB, n - j0);
         const double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
         double* Bj = B + (int64_t)j0 * ldb;
-        int rc = dgemm(c, OP_T, OP_N, nb, k, nb, 1.0, Dj, NB, Bj, ldb, 0.0, Bj, ldb, 0);
+        int rc = dgemm(c, OP_T, OP_N, nb, k, nb, 1.0, Dj, NB, Bj, ldb, 0.0, Bj, ldb, 4);
         if (rc) return rc;
         if (j0 > 0) {
             rc = dgemm(c, OP_T, OP_N, j0, k, nb, -1.0, L + (int64_t)j0 * ldl, ldl, Bj, ldb, 1.0, B, ldb, 0);
@@ -171,26 +323,58 @@ int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* 
     return SFEM_OK;
 }
 
-// Kinv (n x n, ld n) = inv(L L^T); W is an n x n workspace (receives inv(L)).
-int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv) {
-    int64_t tot = (int64_t)n * n;
-    set_identity_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, c->stream>>>(n, W, n);
+__global__ void copy_diag_blocks_kernel(int n, const double* __restrict__ dinv, double* __restrict__ W, int64_t ldw) {
+    // block b of dinv (128 x 128, explicit zeros above the diagonal) -> W[b*128.., b*128..]
+    int b = blockIdx.y;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = t >> 7, cidx = t & (NB - 1);
+    int gr = b * NB + r, gc = b * NB + cidx;
+    if (r < NB && gr < n && gc < n) W[(int64_t)gr * ldw + gc] = dinv[(size_t)b * NB * NB + t];
+}
+
+// W (n x n, ld n) = inv(L) by recursive doubling over the 128-wide diagonal blocks whose inverses potrf left in
+// dinv:  for block size s = 128, 256, ...:  every pair [[L11, 0], [L21, L22]] with inv(L11), inv(L22) known gets
+//   X21 = - inv(L22) (L21 inv(L11)),
+// two batched GEMMs per level (all pairs of a level are independent), log2(n/128) levels instead of n/128 steps.
+// Strictly upper tiles of W are never written nor read.
+int trtri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W) {
+    int nblk = (n + NB - 1) / NB;
+    copy_diag_blocks_kernel<<<dim3(NB * NB / 256, nblk), 256, 0, c->stream>>>(n, dinv, W, n);
     KCHECK(c);
-    for (int j0 = 0; j0 < n; j0 += NB) {
-        int nb = imin(NB, n - j0);
-        int ncols = j0 + nb;    // block row j of inv(L) is non-zero only in its first j0+nb columns
-        const double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
-        double* Wj = W + (int64_t)j0 * n;
-        int rc = dgemm(c, OP_N, OP_N, nb, ncols, nb, 1.0, Dj, NB, Wj, n, 0.0, Wj, n, 0);
-        if (rc) return rc;
-        int m = n - j0 - nb;
-        if (m > 0) {
-            rc = dgemm(c, OP_N, OP_N, m, ncols, nb, -1.0, L + (int64_t)(j0 + nb) * ldl + j0, ldl, Wj, n, 1.0,
-                       W + (int64_t)(j0 + nb) * n, n, 0);
+    if (n <= NB) return SFEM_OK;
+    double* T = (double*)dense_tmp(c, sizeof(double) * (size_t)n * (size_t)((n + 1) / 2 + NB));
+    if (!T) return sfem_fail(c, SFEM_ERR_CUDA, "trtri: temporary allocation failed");
+    for (int64_t s = NB; s < n; s *= 2) {
+        int full = (int)(n / (2 * s));                 // pairs with a complete lower block
+        int64_t rem = n - (int64_t)full * 2 * s;       // ragged tail: a pair exists if rem > s
+        for (int pass = 0; pass < 2; ++pass) {
+            int batch = pass == 0 ? full : (rem > s ? 1 : 0);
+            if (batch == 0) continue;
+            int64_t o = pass == 0 ? 0 : (int64_t)full * 2 * s;
+            int m2 = pass == 0 ? (int)s : (int)(rem - s);
+            const double* L21 = L + (o + s) * ldl + o;
+            const double* X11 = W + o * n + o;
+            const double* X22 = W + (o + s) * n + (o + s);
+            double* X21 = W + (o + s) * n + o;
+            // T = L21 X11   (m2 x s, K = s; X11 lower triangular: k >= n0)
+            int rc = dgemm_batched(c, OP_N, OP_N, m2, (int)s, s, 1.0, L21, ldl, X11, n, 0.0, T, s, 8, batch,
+                                   2 * s * (ldl + 1), 2 * s * ((int64_t)n + 1), s * s);
+            if (rc) return rc;
+            // X21 = - X22 T (m2 x s, K = m2; X22 lower triangular: k <= m0 + tile)
+            rc = dgemm_batched(c, OP_N, OP_N, m2, (int)s, m2, -1.0, X22, n, T, s, 0.0, X21, n, 16, batch,
+                               2 * s * ((int64_t)n + 1), s * s, 2 * s * ((int64_t)n + 1));
             if (rc) return rc;
         }
     }
-    int rc = dgemm(c, OP_T, OP_N, n, n, n, 1.0, W, n, W, n, 0.0, Kinv, n, 3);   // lower tiles, k >= max(m0, n0)
+    return SFEM_OK;
+}
+
+// Kinv (n x n, ld n) = inv(L L^T); W is an n x n workspace (receives inv(L)).
+int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv) {
+    int64_t tot = (int64_t)n * n;
+    int rc = trtri_lower(c, n, L, ldl, dinv, W);
+    if (rc) return rc;
+    rc = dgemm(c, OP_T, OP_N, n, n, n, 1.0, W, n, W, n, 0.0, Kinv, n, 3);   // lower tiles, k >= max(m0, n0)
     if (rc) return rc;
     mirror_lower_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, c->stream>>>(n, Kinv, n);
     KCHECK(c);

@@ -66,6 +66,7 @@ struct sfem_ctx {
     // ---- scratch arena (owned, grows) --------------------------------------------------------------------
     void* scratch = nullptr; size_t scratch_bytes = 0;
     void* pinned = nullptr;          // small pinned host buffer for scalar read-backs
+    void* dense_tmp = nullptr; size_t dense_tmp_bytes = 0;   // panel / trtri temporaries of chol.cu (owned, grows)
 };
 
 int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);
@@ -145,6 +146,9 @@ int spmm_csr(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr, c
 enum { OP_N = 0, OP_T = 1 };
 int dgemm(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only);
+int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
+                  const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int batch,
+                  int64_t strideA, int64_t strideB, int64_t strideC);
 // mg.cu
 int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_t ldz, double* tmp0, void* work);
 void mg_free(sfem_ctx* c);

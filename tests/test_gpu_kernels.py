@@ -26,7 +26,8 @@ def dev(ctx, a, dt=np.float64):
 
 
 @pytest.mark.parametrize("opA,opB", [(1, 0), (0, 0), (0, 1), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (100, 36, 1000), (257, 130, 77), (5, 3, 4099), (64, 200, 20011), (300, 300, 300)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (100, 36, 1000), (257, 130, 77), (5, 3, 4099), (64, 200, 20011), (300, 300, 300),
+                                   (2500, 2300, 130), (1111, 97, 128)])
 def test_dgemm(env, opA, opB, M, N, K):
     _lib, ctx, lib = env
     rng = np.random.default_rng(M * 7 + N * 3 + K + opA * 2 + opB)
@@ -56,7 +57,7 @@ def test_dgemm_strided_and_beta0(env):
         assert np.all(np.isnan(got[:, N:]))
 
 
-@pytest.mark.parametrize("n", [1, 7, 100, 128, 129, 300, 513])
+@pytest.mark.parametrize("n", [1, 7, 100, 128, 129, 257, 300, 384, 513, 640, 1000, 1537])
 def test_cholesky_solve_inverse_logdet(env, n):
     _lib, ctx, lib = env
     rng = np.random.default_rng(n)
