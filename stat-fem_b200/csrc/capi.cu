@@ -1,5 +1,6 @@
 // extern "C" surface of libstatfem_b200.so (see include/statfem_b200.h for the contract of every entry point).
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/statfem_b200.h"
 
 int stiffness_dinv(sfem_ctx* c);
@@ -62,6 +63,8 @@ int sfem_create(sfem_ctx** out, int device, void* cuda_stream) {
     sfem_ctx* c = new sfem_ctx();
     c->device = device;
     c->stream = (cudaStream_t)cuda_stream;
+    if (const char* e = getenv("SFEM_TILE_ROWS")) c->tile_rows = atoi(e);     // tuning knobs of the staged-tile kernels
+    if (const char* e = getenv("SFEM_TILE_SW")) c->tile_sw = atoi(e);
     if (cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
         delete c;
         return SFEM_ERR_CUDA;
@@ -131,7 +134,7 @@ int sfem_profile_num_tags(void) { return TAG_COUNT; }
 const char* sfem_profile_tag_name(int tag) {
     static const char* names[TAG_COUNT] = {"csr_mult_A", "csr_jacobi_A", "csr_resid_A", "spmm_other", "cg_vector",
                                            "mg_transfer_fine", "mg_lattice", "dgemm", "potrf_panel", "gcov_count",
-                                           "gcov_fill", "dense_misc", "setup"};
+                                           "gcov_fill", "dense_misc", "setup", "chol_trsm", "chol_syrk", "trtri", "lauum"};
     return (tag >= 0 && tag < TAG_COUNT) ? names[tag] : "?";
 }
 int sfem_profile_read(sfem_ctx* c, double* ms_out_host, double* bytes_out_host, double* flops_out_host, long long* count_out_host) {

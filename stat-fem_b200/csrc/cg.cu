@@ -5,7 +5,7 @@
 // [n x k] sweep.  Replaces the 2*n_obs sequential PETSc KSP solves of solving_utils.py:49-53 / 139-142 and the mean
 // solve of LinearSolver.py:217.  Preconditioner: Jacobi (precond = 0) or the lattice multigrid V-cycle of mg.cu
 // (precond = 1).  All reductions are two-stage and summed in a fixed order (no floating-point atomics).
-#include "rowops.cuh"
+#include "mg.cuh"
 
 int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
                  const double* X, int64_t ldx, double* R, int64_t ldr, const double* B, int64_t ldb);
@@ -205,22 +205,200 @@ __global__ void __launch_bounds__(RB_THREADS) cg_norm_kernel(int64_t n, int k, c
     block_partials<VEC>(s0, s1, L, k, part_rr, red);
 }
 
+// tile path init: r = B[perm] (rows gathered into the tile numbering), x = 0, p = 0, partial bb
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) cg_init_perm_kernel(int64_t n, int k, const int* __restrict__ perm,
+                                                                 const double* __restrict__ B, int64_t ldb,
+                                                                 double* __restrict__ X, double* __restrict__ R,
+                                                                 double* __restrict__ P, double* __restrict__ part_bb,
+                                                                 int64_t rows_per_block) {
+    __shared__ double red[RB_WARPS][64];
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    double s0 = 0, s1 = 0;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double b0, b1;
+        ld_cols<VEC>(B + (int64_t)perm[row] * ldb, L, b0, b1);
+        st_cols<VEC>(R + row * k, L, b0, b1);
+        st_cols<VEC>(X + row * k, L, 0.0, 0.0);
+        st_cols<VEC>(P + row * k, L, 0.0, 0.0);
+        s0 += b0 * b0; s1 += b1 * b1;
+    }
+    block_partials<VEC>(s0, s1, L, k, part_bb, red);
+}
+
+// X[perm[q]] = Xq[q]  (back to the caller's numbering)
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) cg_scatter_perm_kernel(int64_t n, int k, const int* __restrict__ perm,
+                                                                    const double* __restrict__ Xq, double* __restrict__ X,
+                                                                    int64_t ldx, int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double x0, x1;
+        ld_cols<VEC>(Xq + row * k, L, x0, x1);
+        st_cols<VEC>(X + (int64_t)perm[row] * ldx, L, x0, x1);
+    }
+}
+
+// out[c] = sum_b part[b][c], b ascending within 8 interleaved lanes, then the 8 lane sums in order (deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(int nparts, int k, const double* __restrict__ part, double* __restrict__ out) {
+    __shared__ double sh[8][33];
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    int col = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    if (col < k)
+        for (int b = ty; b < nparts; b += 8) s += part[(int64_t)b * k + col];
+    sh[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && col < k) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += sh[q][tx];
+        out[col] = t;
+    }
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 size_t mg_workspace_bytes(sfem_ctx* c, int k);
+size_t mg_tiles_workspace_bytes(sfem_ctx* c, int k);
+int mg_tiles_fine_chunks(sfem_ctx* c);
+const int* mg_tiles_fine_perm(sfem_ctx* c);
+int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials);
 
 size_t cg_workspace_bytes(sfem_ctx* c, int k, int precond) {
     int64_t n = c->n;
     int kk = k + (k & 1);
     RowGrid g = row_grid(n);
     size_t vec = align256(sizeof(double) * (size_t)n * kk);
-    size_t bytes = 4 * vec;                                       // r, p, q, z
+    size_t bytes = (precond == 1 ? 6 : 4) * vec;                  // r, p, q, z (+ second p, x in the tile numbering)
     bytes += 3 * align256(sizeof(double) * (size_t)g.nblk * kk);  // partials
     bytes += align256(sizeof(double) * 8 * (size_t)kk) + align256(sizeof(int) * ((size_t)kk + 8));
-    if (precond == 1) bytes += mg_workspace_bytes(c, kk);
+    if (precond == 1) {
+        bytes += mg_tiles_workspace_bytes(c, kk);
+        bytes += align256(sizeof(double) * (size_t)mg_tiles_fine_chunks(c) * kk) + align256(sizeof(double) * 2 * (size_t)kk);
+    }
     return bytes + 4096;
+}
+
+// Multigrid-preconditioned path: every vector lives in the tile numbering of the fine level (mg_tiles.cu) and every
+// matrix application is a staged-tile kernel.  Per iteration: one fused direction update + q = A p + p.q pass, one
+// x/r update pass, one V-cycle whose last smoothing sweep also returns r.z.
+static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, int64_t ldx, double rtol,
+                                double atol, int max_it, int* iters_out, double* relres_out_host, void* work) {
+    const int64_t n = c->n;
+    RowGrid g = row_grid(n);
+    const int kk = k + (k & 1);
+    unsigned char* w = (unsigned char*)work;
+    size_t vec = align256(sizeof(double) * (size_t)n * kk);
+    double* R = (double*)w; w += vec;
+    double* Pa = (double*)w; w += vec;
+    double* Pb = (double*)w; w += vec;
+    double* Q = (double*)w; w += vec;
+    double* Z = (double*)w; w += vec;
+    double* Xq = (double*)w; w += vec;
+    size_t psz = align256(sizeof(double) * (size_t)g.nblk * kk);
+    double* part0 = (double*)w; w += psz;
+    double* part1 = (double*)w; w += psz;
+    w += psz;
+    Scal s;
+    double* sc = (double*)w; w += align256(sizeof(double) * 8 * (size_t)kk);
+    s.rho = sc; s.alpha = sc + k; s.beta = sc + 2 * k; s.bb = sc + 3 * k; s.rr = sc + 4 * k; s.tol2 = sc + 5 * k;
+    double* relres_dev = sc + 6 * k;
+    s.active = (int*)w; s.n_active = s.active + k;
+    w += align256(sizeof(int) * ((size_t)kk + 8));
+    const int nch = mg_tiles_fine_chunks(c);
+    double* part_tile = (double*)w; w += align256(sizeof(double) * (size_t)nch * kk);
+    double* red = (double*)w; w += align256(sizeof(double) * 2 * (size_t)kk);
+    void* mgwork = w;
+    const int* perm = mg_tiles_fine_perm(c);
+    MGLevel* L0 = c->mg[0];
+
+    bool v2 = (k % 2 == 0) && (ldx % 2 == 0) && (ldb % 2 == 0) &&
+              ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(work)) % 16 == 0);
+    dim3 grid(g.nblk, v2 ? (k + 63) / 64 : (k + 31) / 32);
+    int sb = (k + 127) / 128;
+    int rb = (k + 31) / 32;
+    int* h_nact = (int*)c->pinned;
+#define LAUNCH_T(passes, kern, ...)                                                    \
+    do {                                                                               \
+        ProfScope _ps(c, TAG_CG_VEC, (passes) * 8.0 * (double)n * k, 0.0);             \
+        if (v2) kern<2> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);              \
+        else kern<1> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);                 \
+        KCHECK(c);                                                                     \
+    } while (0)
+    CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(sc, 0, sizeof(double) * 8 * (size_t)kk, c->stream));
+    LAUNCH_T(4, cg_init_perm_kernel, n, k, perm, B, ldb, Xq, R, Pa, part0, g.rows_per_block);
+    cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, nullptr, s, rtol, atol);
+    KCHECK(c);
+    int rc = mg_apply_tiles(c, k, R, Z, Q, Pb, mgwork, part_tile);
+    if (rc) return rc;
+    reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red);
+    KCHECK(c);
+    cg_rho_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, s);
+    KCHECK(c);
+    CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int it = 0;
+    int nact = *h_nact;
+    double* pin = Pa;
+    double* pout = Pb;
+    while (nact > 0 && it < max_it) {
+        {   // p = z + beta p ; q = A p ; sigma = p.q
+            TileArgs a; a.k = k; a.X = Z; a.ldx = k; a.Y = Q; a.ldy = k; a.Pin = pin; a.Pout = pout; a.ldp = k;
+            a.beta = s.beta; a.partials = part_tile;
+            rc = tileop_apply(c, TAG_CSR_MULT, L0->tA, TM_PMULT_DOT, a,
+                              32.0 * (double)n * k + 10.0 * (double)L0->tA.nnz + 4.0 * (double)n);
+            if (rc) return rc;
+        }
+        reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red);
+        KCHECK(c);
+        cg_alpha_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, s);
+        KCHECK(c);
+        {
+            ProfScope _ps(c, TAG_CG_VEC, 6 * 8.0 * (double)n * k, 0.0);
+            if (v2) cg_update_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, pout, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
+            else cg_update_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, pout, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
+            KCHECK(c);
+        }
+        rc = mg_apply_tiles(c, k, R, Z, Q, pin, mgwork, part_tile);     // Q and the previous direction are free now
+        if (rc) return rc;
+        reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red + kk);
+        KCHECK(c);
+        reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(g.nblk, k, part1, red);
+        KCHECK(c);
+        CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
+        cg_beta_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, red + kk, s);
+        KCHECK(c);
+        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        nact = *h_nact;
+        std::swap(pin, pout);
+        ++it;
+    }
+    if (iters_out) *iters_out = it;
+    LAUNCH_T(2, cg_scatter_perm_kernel, n, k, perm, Xq, X, ldx, g.rows_per_block);
+    {   // true residual || B - A X || / || B || per column, in the caller's numbering
+        rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, X, ldx, R, k, B, ldb);
+        if (rc) return rc;
+        LAUNCH_T(1, cg_norm_kernel, n, k, R, part0, g.rows_per_block);
+        cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, relres_dev);
+        KCHECK(c);
+        if (relres_out_host)
+            CUDA_TRY(c, cudaMemcpyAsync(relres_out_host, relres_dev, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+#undef LAUNCH_T
+    if (nact > 0) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: %d of %d columns not converged after %d iterations", nact, k, it);
+    return SFEM_OK;
 }
 
 // Solve A X = B for k columns.  X (ldx) receives the solution.  `work` must hold cg_workspace_bytes().
@@ -233,6 +411,7 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     if (work_bytes < cg_workspace_bytes(c, k, precond))
         return sfem_fail(c, SFEM_ERR_ARG, "solve_block: workspace too small (%zu < %zu)", work_bytes,
                          cg_workspace_bytes(c, k, precond));
+    if (precond == 1) return cg_solve_block_tiles(c, k, B, ldb, X, ldx, rtol, atol, max_it, iters_out, relres_out_host, work);
     // internal blocks use leading dimension k (must be even for the double2 path: pad by requiring k even or VEC=1)
     RowGrid g = row_grid(n);
     unsigned char* w = (unsigned char*)work;

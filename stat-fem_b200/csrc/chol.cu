@@ -280,9 +280,12 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
         if (m > 0) {
             double* A21 = A + (int64_t)(j0 + nb) * lda + j0;
             double* A22 = A + (int64_t)(j0 + nb) * lda + (j0 + nb);
+            c->dgemm_tag = TAG_CHOL_TRSM;
             int rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);   // T = A21 inv(L_jj)^T
+            c->dgemm_tag = TAG_CHOL_SYRK;
             if (rc) return rc;
             rc = dgemm(c, OP_N, OP_T, m, m, nb, -1.0, T, NB, T, NB, 1.0, A22, lda, 1);             // SYRK, lower tiles
+            c->dgemm_tag = TAG_DGEMM;
             if (rc) return rc;
             CUDA_TRY(c, cudaMemcpy2DAsync(A21, sizeof(double) * lda, T, sizeof(double) * NB, sizeof(double) * nb, m,
                                           cudaMemcpyDeviceToDevice, c->stream));
@@ -372,9 +375,11 @@ int trtri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* 
 // Kinv (n x n, ld n) = inv(L L^T); W is an n x n workspace (receives inv(L)).
 int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv) {
     int64_t tot = (int64_t)n * n;
+    c->dgemm_tag = TAG_TRTRI;
     int rc = trtri_lower(c, n, L, ldl, dinv, W);
-    if (rc) return rc;
-    rc = dgemm(c, OP_T, OP_N, n, n, n, 1.0, W, n, W, n, 0.0, Kinv, n, 3);   // lower tiles, k >= max(m0, n0)
+    c->dgemm_tag = TAG_LAUUM;
+    if (rc == SFEM_OK) rc = dgemm(c, OP_T, OP_N, n, n, n, 1.0, W, n, W, n, 0.0, Kinv, n, 3);   // lower tiles, k >= max(m0, n0)
+    c->dgemm_tag = TAG_DGEMM;
     if (rc) return rc;
     mirror_lower_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, c->stream>>>(n, Kinv, n);
     KCHECK(c);

@@ -21,6 +21,7 @@ struct sfem_ctx {
     cudaStream_t stream = nullptr;
     char err[1024] = {0};
     long long launches = 0;          // kernels launched by this library (bench.py's gpu_launches)
+    int dgemm_tag = 7;               // profile family charged for dgemm launches (chol.cu switches it per phase)
 
     // ---- stiffness A (caller-owned CSR; identity Dirichlet rows/cols) -------------------------------
     int64_t n = 0;
@@ -52,6 +53,8 @@ struct sfem_ctx {
     std::vector<MGLevel*> mg;
     int mg_nu_pre = 2, mg_nu_post = 2;
     double mg_omega = 0.8;
+    int tile_rows = 0;               // rows per fine-level chunk of the staged-tile operators (0: default)
+    int tile_sw = 0;                 // slab width override for the tile kernels (0: automatic, 32: force 32 columns)
 
     // ---- optional per-kernel-family timing (CUDA events on the launch stream) + algorithmic work counters ------
     unsigned prof_mask = 0;
@@ -104,7 +107,11 @@ enum {
     TAG_GCOV_FILL = 10,
     TAG_DENSE_MISC = 11,  // kernel matrix, gradient reductions, small vector kernels
     TAG_SETUP = 12,       // multigrid setup, cell lists, scans
-    TAG_COUNT = 13
+    TAG_CHOL_TRSM = 13,   // dgemm: panel solve of the blocked Cholesky
+    TAG_CHOL_SYRK = 14,   // dgemm: trailing update of the blocked Cholesky
+    TAG_TRTRI = 15,       // dgemm: recursive-doubling triangular inverse
+    TAG_LAUUM = 16,       // dgemm: inv(L)^T inv(L)
+    TAG_COUNT = 17
 };
 
 struct ProfScope {

@@ -325,9 +325,9 @@ int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double
     p.kchunk = kchunk > 0 ? kchunk : BK;
     bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0) &&
                 (lda % 2 == 0) && (ldb % 2 == 0);
-    ProfScope ps(c, TAG_DGEMM, batch * 8.0 * ((double)M * K + (double)K * N + (double)M * N * (beta != 0.0 ? 2.0 : 1.0)),
+    ProfScope ps(c, c->dgemm_tag, batch * 8.0 * ((double)M * K + (double)K * N + (double)M * N * (beta != 0.0 ? 2.0 : 1.0)),
                  batch * 2.0 * (double)M * N * (double)K *
-                     ((flags & 3) == 3 ? 1.0 / 3.0 : ((flags & 1) ? 0.5 : 1.0)) * ((flags & 24) ? 0.5 : 1.0));
+                     ((flags & 3) == 3 ? 1.0 / 6.0 : ((flags & 1) ? 0.5 : 1.0)) * ((flags & 24) ? 0.5 : 1.0));
     dim3 grid(tiles, batch, splits);
     bool akm = (opA == OP_T), bkm = (opB == OP_N);
     int rc = tb == 128 ? launch_layout<128>(c, p, al16, grid, akm, bkm) : launch_layout<64>(c, p, al16, grid, akm, bkm);

@@ -11,7 +11,7 @@
 //
 // This is the replacement for the sparse direct solve behind Firedrake's LinearSolver (LinearSolver.py:136-140,
 // solving_utils.py:51,53): unpreconditioned CG needs ~3.7*N_side iterations on these meshes (SURVEY finding 5).
-#include "rowops.cuh"
+#include "mg.cuh"
 #include <cmath>
 
 int build_cell_list(sfem_ctx* c, const int* cell_of, int64_t n, int ncell, int** cell_start_out, int** cell_nodes_out);
@@ -21,57 +21,7 @@ int csr_jacobi(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, c
 int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
                  const double* X, int64_t ldx, double* R, int64_t ldr, const double* B, int64_t ldb);
 
-struct MGLevel {
-    int kind = 1;                 // 0 = CSR fine level, 1 = lattice
-    int64_t n = 0;
-    int d = 1;
-    int m[3] = {1, 1, 1};         // lattice nodes per direction
-    int S = 5;                    // stencil entries per node (5^d)
-    double* stencil = nullptr;    // [n][S]
-    double* dinv = nullptr;       // [n]
-    unsigned char* constrained = nullptr;   // [n]  (level 0: Dirichlet mask, owned copy)
-    // level 0 -> level 1 transfer
-    int* cidx = nullptr;          // [n] lattice cell of each fine node
-    double* frac = nullptr;       // [n][d] position inside the cell, in [0,1]
-    int* cell_start = nullptr;
-    int* cell_nodes = nullptr;
-    // lattice -> next lattice
-    int coarsen[3] = {0, 0, 0};
-    double* dense_inv = nullptr;  // coarsest: [n][n]
-};
-
 namespace {
-
-struct Lat {
-    int d, m0, m1, m2, S;
-    int64_t n;
-};
-__host__ __device__ inline Lat make_lat(int d, const int* m) {
-    Lat L;
-    L.d = d; L.m0 = m[0]; L.m1 = d > 1 ? m[1] : 1; L.m2 = d > 2 ? m[2] : 1;
-    L.S = d == 1 ? 5 : (d == 2 ? 25 : 125);
-    L.n = (int64_t)L.m0 * L.m1 * L.m2;
-    return L;
-}
-__device__ __forceinline__ void lat_decode(const Lat& L, int node, int& i0, int& i1, int& i2) {
-    i0 = node % L.m0;
-    int t = node / L.m0;
-    i1 = t % L.m1;
-    i2 = t / L.m1;
-}
-__device__ __forceinline__ int lat_index(const Lat& L, int i0, int i1, int i2) { return i0 + L.m0 * (i1 + L.m1 * i2); }
-// stencil slot <-> offset
-__device__ __forceinline__ int slot_of(int d, int o0, int o1, int o2) {
-    int s = o0 + 2;
-    if (d > 1) s += 5 * (o1 + 2);
-    if (d > 2) s += 25 * (o2 + 2);
-    return s;
-}
-__device__ __forceinline__ void slot_decode(int d, int s, int& o0, int& o1, int& o2) {
-    o0 = s % 5 - 2;
-    o1 = d > 1 ? (s / 5) % 5 - 2 : 0;
-    o2 = d > 2 ? s / 25 - 2 : 0;
-}
 
 // ---------------------------------------------------------------------------------------------- setup kernels
 struct FineXfer {
@@ -110,13 +60,6 @@ __global__ void csr_dinv_kernel(int64_t n, const int64_t* __restrict__ ptr, cons
     for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p)
         if (idx[p] == i) dg += val[p];
     dinv[i] = dg != 0.0 ? 1.0 / dg : 1.0;
-}
-
-__device__ __forceinline__ double corner_weight(int d, const double* __restrict__ t, int beta) {
-    double w = (beta & 1) ? t[0] : 1.0 - t[0];
-    if (d > 1) w *= (beta & 2) ? t[1] : 1.0 - t[1];
-    if (d > 2) w *= (beta & 4) ? t[2] : 1.0 - t[2];
-    return w;
 }
 
 // level-1 lattice node is constrained iff its best-supported fine node is a Dirichlet node (or it has no support)
@@ -212,13 +155,6 @@ __global__ void l1_galerkin_kernel(Lat L, int d, int warps_per_block, const int6
     }
 }
 
-// lattice -> coarser lattice
-struct LatPair {
-    Lat F, C;
-    int d;
-    int co[3];     // direction coarsened?
-};
-
 __global__ void lat_constrained_kernel(LatPair P, const unsigned char* __restrict__ cf, unsigned char* __restrict__ cc) {
     int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= P.C.n) return;
@@ -227,8 +163,6 @@ __global__ void lat_constrained_kernel(LatPair P, const unsigned char* __restric
     int f0 = P.co[0] ? 2 * I0 : I0, f1 = P.co[1] ? 2 * I1 : I1, f2 = P.co[2] ? 2 * I2 : I2;
     cc[node] = cf[lat_index(P.F, f0, f1, f2)];
 }
-
-__device__ __forceinline__ double w1d(int co, int e) { return co ? (e == 0 ? 1.0 : 0.5) : 1.0; }
 
 // Galerkin for lattice levels: one thread per (coarse node, coarse offset)
 __global__ void lat_galerkin_kernel(LatPair P, const double* __restrict__ sf, const unsigned char* __restrict__ cf,
@@ -554,19 +488,14 @@ __global__ void __launch_bounds__(RB_THREADS) dense_apply_kernel(int n, int k, c
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-LatPair make_pair(const MGLevel* F, const MGLevel* C) {
-    LatPair P;
-    P.F = make_lat(F->d, F->m);
-    P.C = make_lat(C->d, C->m);
-    P.d = F->d;
-    for (int q = 0; q < 3; ++q) P.co[q] = F->coarsen[q];
-    return P;
-}
-
 }  // namespace
+
+void mg_tiles_free(MGLevel* L);
+int mg_build_tiles(sfem_ctx* c);
 
 void mg_free(sfem_ctx* c) {
     for (MGLevel* L : c->mg) {
+        mg_tiles_free(L);
         if (L->stencil) cudaFree(L->stencil);
         if (L->dinv) cudaFree(L->dinv);
         if (L->constrained) cudaFree(L->constrained);
@@ -696,7 +625,7 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
         KCHECK(c);
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return SFEM_OK;
+    return mg_build_tiles(c);
 }
 
 // workspace: for every lattice level: bufA, bufB, b  (each n_l x k)
