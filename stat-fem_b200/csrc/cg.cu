@@ -269,9 +269,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t mg_workspace_bytes(sfem_ctx* c, int k);
 size_t mg_tiles_workspace_bytes(sfem_ctx* c, int k);
-int mg_tiles_fine_chunks(sfem_ctx* c);
 const int* mg_tiles_fine_perm(sfem_ctx* c);
-int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials);
+int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials, int* nparts);
 
 size_t cg_workspace_bytes(sfem_ctx* c, int k, int precond) {
     int64_t n = c->n;
@@ -283,14 +282,14 @@ size_t cg_workspace_bytes(sfem_ctx* c, int k, int precond) {
     bytes += align256(sizeof(double) * 8 * (size_t)kk) + align256(sizeof(int) * ((size_t)kk + 8));
     if (precond == 1) {
         bytes += mg_tiles_workspace_bytes(c, kk);
-        bytes += align256(sizeof(double) * (size_t)mg_tiles_fine_chunks(c) * kk) + align256(sizeof(double) * 2 * (size_t)kk);
+        bytes += align256(sizeof(double) * (size_t)TILE_MAX_PARTS * kk) + align256(sizeof(double) * 2 * (size_t)kk);
     }
     return bytes + 4096;
 }
 
 // Multigrid-preconditioned path: every vector lives in the tile numbering of the fine level (mg_tiles.cu) and every
-// matrix application is a staged-tile kernel.  Per iteration: one fused direction update + q = A p + p.q pass, one
-// x/r update pass, one V-cycle whose last smoothing sweep also returns r.z.
+// matrix application is a staged-tile kernel.  Per iteration: the direction update, q = A p with p.q fused, the x/r
+// update with r.r fused, and one V-cycle whose last smoothing sweep also returns r.z.
 static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, int64_t ldx, double rtol,
                                 double atol, int max_it, int* iters_out, double* relres_out_host, void* work) {
     const int64_t n = c->n;
@@ -314,8 +313,8 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
     double* relres_dev = sc + 6 * k;
     s.active = (int*)w; s.n_active = s.active + k;
     w += align256(sizeof(int) * ((size_t)kk + 8));
-    const int nch = mg_tiles_fine_chunks(c);
-    double* part_tile = (double*)w; w += align256(sizeof(double) * (size_t)nch * kk);
+    int nch = 0;
+    double* part_tile = (double*)w; w += align256(sizeof(double) * (size_t)TILE_MAX_PARTS * kk);
     double* red = (double*)w; w += align256(sizeof(double) * 2 * (size_t)kk);
     void* mgwork = w;
     const int* perm = mg_tiles_fine_perm(c);
@@ -339,7 +338,7 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
     LAUNCH_T(4, cg_init_perm_kernel, n, k, perm, B, ldb, Xq, R, Pa, part0, g.rows_per_block);
     cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, nullptr, s, rtol, atol);
     KCHECK(c);
-    int rc = mg_apply_tiles(c, k, R, Z, Q, Pb, mgwork, part_tile);
+    int rc = mg_apply_tiles(c, k, R, Z, Q, Pb, mgwork, part_tile, &nch);
     if (rc) return rc;
     reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red);
     KCHECK(c);
@@ -349,14 +348,17 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     int it = 0;
     int nact = *h_nact;
-    double* pin = Pa;
-    double* pout = Pb;
     while (nact > 0 && it < max_it) {
-        {   // p = z + beta p ; q = A p ; sigma = p.q
-            TileArgs a; a.k = k; a.X = Z; a.ldx = k; a.Y = Q; a.ldy = k; a.Pin = pin; a.Pout = pout; a.ldp = k;
-            a.beta = s.beta; a.partials = part_tile;
-            rc = tileop_apply(c, TAG_CSR_MULT, L0->tA, TM_PMULT_DOT, a,
-                              32.0 * (double)n * k + 10.0 * (double)L0->tA.nnz + 4.0 * (double)n);
+        {   // p = z + beta p   (beta = 0 on the first pass: p was zeroed)
+            ProfScope _ps(c, TAG_CG_VEC, 3 * 8.0 * (double)n * k, 0.0);
+            if (v2) cg_pupdate_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.beta, Z, nullptr, Pa, g.rows_per_block);
+            else cg_pupdate_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.beta, Z, nullptr, Pa, g.rows_per_block);
+            KCHECK(c);
+        }
+        {   // q = A p ; sigma = p.q
+            TileArgs a; a.k = k; a.X = Pa; a.ldx = k; a.Y = Q; a.ldy = k; a.partials = part_tile;
+            rc = tileop_apply(c, TAG_CSR_MULT, L0->tA, TM_MULT_DOT, a,
+                              16.0 * (double)n * k + 10.0 * (double)L0->tA.nnz + 4.0 * (double)n, &nch);
             if (rc) return rc;
         }
         reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red);
@@ -365,11 +367,11 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         KCHECK(c);
         {
             ProfScope _ps(c, TAG_CG_VEC, 6 * 8.0 * (double)n * k, 0.0);
-            if (v2) cg_update_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, pout, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
-            else cg_update_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, pout, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
+            if (v2) cg_update_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, Pa, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
+            else cg_update_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, Pa, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
             KCHECK(c);
         }
-        rc = mg_apply_tiles(c, k, R, Z, Q, pin, mgwork, part_tile);     // Q and the previous direction are free now
+        rc = mg_apply_tiles(c, k, R, Z, Q, Pb, mgwork, part_tile, &nch);      // Q is free again after the update
         if (rc) return rc;
         reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red + kk);
         KCHECK(c);
@@ -381,7 +383,6 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         nact = *h_nact;
-        std::swap(pin, pout);
         ++it;
     }
     if (iters_out) *iters_out = it;

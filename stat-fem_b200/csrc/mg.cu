@@ -39,6 +39,10 @@ __global__ void fine_locate_kernel(FineXfer f, int* __restrict__ cidx, double* _
     const int mm[3] = {f.L1.m0, f.L1.m1, f.L1.m2};
     for (int k = 0; k < f.d; ++k) {
         double u = (f.coords[i * f.d + k] - f.lo[k]) * f.invH[k];
+        // snap to lattice nodes and cell midpoints: the transfer weights of aligned meshes must be exactly 0, 1/2, 1
+        // (a weight of 1e-16 would still count as a coupling and fill the coarse stencils)
+        double u2 = rint(2.0 * u);
+        if (fabs(2.0 * u - u2) < 1e-9 * (1.0 + fabs(u2))) u = 0.5 * u2;
         int cell = (int)floor(u);
         int maxc = mm[k] - 2;
         if (cell < 0) cell = 0;

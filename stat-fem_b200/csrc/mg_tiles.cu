@@ -9,8 +9,8 @@
 //   prolongation   x += P x'          (TM_MULT_ADD)     post-smoothing          (TM_JACOBI, the last sweep on the
 //                                                        fine level also returns the r.z partials for CG)
 // Level 0 numbering: fine unknowns sorted by the Morton code of the level-1 lattice cell they sit in (a counting
-// sort, ascending original index inside a cell); 64 consecutive unknowns ~ a 4x4 block of cells.
-// Lattice levels: nodes ordered tile by tile (8x8 in 2-D, 4x4x4 in 3-D; the 2^p+1-th node of a direction forms a
+// sort, ascending original index inside a cell); 32 consecutive unknowns ~ a 4x2 block of cells.
+// Lattice levels: nodes ordered tile by tile (8x4 in 2-D, 4x4x2 in 3-D; the 2^p+1-th node of a direction forms a
 // thin tile of its own), one chunk per tile.  The coarsest level (dense inverse) keeps its lexicographic numbering.
 #include "mg.cuh"
 
@@ -67,7 +67,7 @@ struct TileGeom {
 TileGeom make_geom(const MGLevel* L) {
     TileGeom g;
     g.d = L->d;
-    const int T2[3] = {8, 8, 1}, T3[3] = {4, 4, 4}, T1[3] = {64, 1, 1};
+    const int T2[3] = {8, 4, 1}, T3[3] = {4, 4, 2}, T1[3] = {32, 1, 1};
     for (int k = 0; k < 3; ++k) {
         g.m[k] = k < L->d ? L->m[k] : 1;
         g.T[k] = L->d == 1 ? T1[k] : (L->d == 2 ? T2[k] : T3[k]);
@@ -355,7 +355,7 @@ int mg_build_tiles(sfem_ctx* c) {
         TRY_CUDA(cudaMalloc(&L0->iperm, sizeof(int) * (size_t)n));
         invert_perm_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(n, L0->perm, L0->iperm);
         c->launches++;
-        const int R0 = c->tile_rows > 0 ? c->tile_rows : 64;
+        const int R0 = c->tile_rows > 0 ? c->tile_rows : 32;
         nchunks[0] = (int)cdiv64(n, R0);
         max_rows[0] = R0;
         TRY_CUDA(cudaMalloc(&chunk_ptr[0], sizeof(int) * ((size_t)nchunks[0] + 1)));
@@ -397,6 +397,7 @@ int mg_build_tiles(sfem_ctx* c) {
     {
         GenA0 g{c->A_ptr, c->A_idx, c->A_val, L0->perm, L0->iperm};
         TRY_RC(build_op(c, g, n, n, chunk_ptr[0], nchunks[0], max_rows[0], &L0->tA));
+        TRY_RC(tileop_scale_columns(c, &L0->tA, L0->dinv_t));
     }
     {
         MGLevel* L1 = c->mg[1];
@@ -413,6 +414,7 @@ int mg_build_tiles(sfem_ctx* c) {
         if (!(coarsest && L->dense_inv)) {
             GenLatA ga{lat, L->d, L->stencil, L->perm, L->iperm};
             TRY_RC(build_op(c, ga, L->n, L->n, chunk_ptr[l], nchunks[l], max_rows[l], &L->tA));
+            TRY_RC(tileop_scale_columns(c, &L->tA, L->dinv_t));
         }
         if (!coarsest) {
             MGLevel* C = c->mg[l + 1];
@@ -430,7 +432,6 @@ int mg_build_tiles(sfem_ctx* c) {
     return SFEM_OK;
 }
 
-int mg_tiles_fine_chunks(sfem_ctx* c) { return c->mg.empty() ? 0 : c->mg[0]->tA.nchunks; }
 const int* mg_tiles_fine_perm(sfem_ctx* c) { return c->mg.empty() ? nullptr : c->mg[0]->perm; }
 
 // workspace: for every lattice level: x0, x1, b  (each n_l x k)
@@ -443,8 +444,8 @@ size_t mg_tiles_workspace_bytes(sfem_ctx* c, int k) {
 static double op_bytes(const TileOp& op, double vec_rows, int k) { return 8.0 * vec_rows * k + 10.0 * (double)op.nnz + 4.0 * (double)op.nrows; }
 
 // Z = M^-1 R (one V-cycle) in the tile numbering of level 0.  R, Z, T0, T1: [n x k] with leading dimension k (k even
-// or all buffers 8-byte aligned only).  dot_partials (nullable): [fine chunks][k] partial sums of R .* Z.
-int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials) {
+// or all buffers 8-byte aligned only).  dot_partials (nullable): [TILE_MAX_PARTS][k] partial sums of R .* Z, *nparts rows used.
+int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials, int* nparts) {
     const int nl = (int)c->mg.size();
     if (nl < 2 || c->mg[0]->tA.nrows == 0) return sfem_fail(c, SFEM_ERR_STATE, "mg_apply: hierarchy not built");
     const int nu = c->mg_nu_pre;
@@ -561,7 +562,8 @@ int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, d
             double* dst = last ? Z : oth0;
             TileArgs a; a.k = k; a.X = cur0; a.ldx = k; a.Y = dst; a.ldy = k; a.B = R; a.ldb = k; a.dinv = L->dinv_t;
             a.partials = dot_partials;
-            rc = tileop_apply(c, TAG_CSR_JACOBI, L->tA, (last && dot_partials) ? TM_JACOBI_DOT : TM_JACOBI, a, op_bytes(L->tA, 3.0 * L->n, k));
+            rc = tileop_apply(c, TAG_CSR_JACOBI, L->tA, (last && dot_partials) ? TM_JACOBI_DOT : TM_JACOBI, a, op_bytes(L->tA, 3.0 * L->n, k),
+                              last ? nparts : nullptr);
             if (rc) return rc;
             std::swap(cur0, oth0);
         }

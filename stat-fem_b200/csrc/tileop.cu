@@ -1,6 +1,7 @@
 // Staged-tile sparse operators: format builder and the fused apply kernels (see tileop.cuh).
 #include "tileop.cuh"
 #include <climits>
+#include <cstdlib>
 
 template <typename T>
 int exclusive_scan(sfem_ctx* c, const T* in, int64_t n, T* out, T* sums);
@@ -62,328 +63,384 @@ __device__ __forceinline__ int lower_bound_dev(const int* a, int n, int key) {
     return lo;
 }
 
-// pass 0: per-chunk counts.  stats[0] = max need, stats[1] = max entries, stats[2] = error flag
+// pass 0: per-chunk counts.  stats[0] = max need, stats[1] = max padded row width, stats[2] = error flag
 __global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(const int* __restrict__ chunk_ptr, const int64_t* __restrict__ ptr,
-                                                                const int32_t* __restrict__ idx, int* __restrict__ need_cnt,
-                                                                int* __restrict__ stats) {
+                                                                const int32_t* __restrict__ idx, int* __restrict__ stats) {
     extern __shared__ int tb_smem[];
     int* keys = tb_smem;
     int* uniq = tb_smem + TB_MAXENT;
     __shared__ int scan[TB_THREADS];
+    __shared__ int wmax;
     int cidx = blockIdx.x;
     int r0 = chunk_ptr[cidx], r1 = chunk_ptr[cidx + 1];
     int64_t e0 = ptr[r0], e1 = ptr[r1];
     if (e1 - e0 > TB_MAXENT) {
-        if (threadIdx.x == 0) { stats[2] = 1; need_cnt[cidx] = 0; }
+        if (threadIdx.x == 0) stats[2] = 1;
         return;
     }
+    if (threadIdx.x == 0) wmax = 0;
+    __syncthreads();
+    for (int r = r0 + threadIdx.x; r < r1; r += TB_THREADS) atomicMax(&wmax, (int)(ptr[r + 1] - ptr[r]));
     int ne = (int)(e1 - e0);
     int nu = chunk_distinct_columns(idx, e0, ne, keys, uniq, scan);
     if (threadIdx.x == 0) {
-        need_cnt[cidx] = nu;
         atomicMax(&stats[0], nu);
-        atomicMax(&stats[1], ne);
+        atomicMax(&stats[1], (wmax + 1) & ~1);
         if (nu > 65535) stats[2] = 1;
     }
 }
 
-// pass 1: staged-row lists, slot indices, row pointers, self slots
-__global__ void __launch_bounds__(TB_THREADS) tile_fill_kernel(int64_t nrows, int square, const int* __restrict__ chunk_ptr,
-                                                               const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                               const double* __restrict__ val, const int* __restrict__ need_ptr,
-                                                               int* __restrict__ need_rows, int* __restrict__ ent_ptr,
-                                                               unsigned short* __restrict__ ent_col, double* __restrict__ ent_val,
-                                                               unsigned short* __restrict__ self_slot, int* __restrict__ meta) {
+// pass 1: fixed-stride chunk records: descriptor, staged-row list, and the entries as a per-chunk ELL block
+// (every row padded to the chunk's even width W with zero entries pointing at slot 0)
+__global__ void __launch_bounds__(TB_THREADS) tile_fill_kernel(int square, int R, int dl, int n4, int e8,
+                                                               const int* __restrict__ chunk_ptr, const int64_t* __restrict__ ptr,
+                                                               const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                                               int* __restrict__ desc, int* __restrict__ need,
+                                                               unsigned short* __restrict__ ecol, double* __restrict__ eval) {
     extern __shared__ int tb_smem[];
     int* keys = tb_smem;
     int* uniq = tb_smem + TB_MAXENT;
     __shared__ int scan[TB_THREADS];
+    __shared__ int wmax;
     int cidx = blockIdx.x;
-    int r0 = chunk_ptr[cidx], r1 = chunk_ptr[cidx + 1];
+    int r0 = chunk_ptr[cidx], r1 = chunk_ptr[cidx + 1], nr = r1 - r0;
     int64_t e0 = ptr[r0], e1 = ptr[r1];
     int ne = (int)(e1 - e0);
+    if (threadIdx.x == 0) wmax = 0;
+    __syncthreads();
+    for (int r = r0 + threadIdx.x; r < r1; r += TB_THREADS) atomicMax(&wmax, (int)(ptr[r + 1] - ptr[r]));
     int nu = chunk_distinct_columns(idx, e0, ne, keys, uniq, scan);
-    int n0 = need_ptr[cidx];
-    for (int t = threadIdx.x; t < nu; t += TB_THREADS) need_rows[n0 + t] = uniq[t];
-    for (int t = threadIdx.x; t < ne; t += TB_THREADS) {
-        ent_col[e0 + t] = (unsigned short)lower_bound_dev(uniq, nu, idx[e0 + t]);
-        ent_val[e0 + t] = val[e0 + t];
+    const int W = (wmax + 1) & ~1;
+    int* dsc = desc + (size_t)cidx * dl;
+    int* nd = need + (size_t)cidx * n4;
+    unsigned short* ec = ecol + (size_t)cidx * e8;
+    double* ev = eval + (size_t)cidx * e8;
+    for (int t = threadIdx.x; t < nu; t += TB_THREADS) nd[t] = uniq[t];
+    for (int t = threadIdx.x; t < nr * W; t += TB_THREADS) {
+        int r = t / W, w = t - r * W;
+        int64_t p = ptr[r0 + r] + w;
+        if (p < ptr[r0 + r + 1]) {
+            ec[t] = (unsigned short)lower_bound_dev(uniq, nu, idx[p]);
+            ev[t] = val[p];
+        } else {
+            ec[t] = 0;
+            ev[t] = 0.0;
+        }
     }
-    for (int r = r0 + threadIdx.x; r < r1; r += TB_THREADS) {
-        ent_ptr[r] = (int)ptr[r];
+    unsigned short* selfs = reinterpret_cast<unsigned short*>(dsc + 8);
+    for (int r = threadIdx.x; r < nr; r += TB_THREADS) {
         unsigned short s = 0xffff;
         if (square) {
-            int p = lower_bound_dev(uniq, nu, r);
-            if (p < nu && uniq[p] == r) s = (unsigned short)p;
+            int p = lower_bound_dev(uniq, nu, r0 + r);
+            if (p < nu && uniq[p] == r0 + r) s = (unsigned short)p;
         }
-        self_slot[r] = s;
+        selfs[r] = s;
     }
-    if (r1 == nrows && threadIdx.x == 0) ent_ptr[nrows] = (int)ptr[nrows];
     if (threadIdx.x == 0) {
         // own rows occupy consecutive slots iff every one of them is referenced (sorted distinct integers)
-        int own = -1;
-        if (square && r1 > r0) {
+        int own = 0, nown = 0;
+        if (square && nr > 0) {
             int p = lower_bound_dev(uniq, nu, r0);
-            int nr = r1 - r0;
-            if (p + nr <= nu && uniq[p] == r0 && uniq[p + nr - 1] == r1 - 1) own = p;
+            if (p + nr <= nu && uniq[p] == r0 && uniq[p + nr - 1] == r1 - 1) { own = p; nown = nr; }
         }
-        int* mt = meta + (size_t)cidx * 8;
-        mt[0] = r0; mt[1] = r1 - r0; mt[2] = n0; mt[3] = nu; mt[4] = (int)e0; mt[5] = ne; mt[6] = own; mt[7] = 0;
+        dsc[0] = r0; dsc[1] = nr; dsc[2] = nu; dsc[3] = W; dsc[4] = own; dsc[5] = nown; dsc[6] = 0; dsc[7] = 0;
+    }
+}
+
+__global__ void tile_scale_kernel(int nchunks, int dl, int n4, int e8, const int* __restrict__ desc, const int* __restrict__ need,
+                                  const unsigned short* __restrict__ ecol, const double* __restrict__ eval,
+                                  const double* __restrict__ dinv, double* __restrict__ out) {
+    int cidx = blockIdx.x;
+    int ne = desc[(size_t)cidx * dl + 1] * desc[(size_t)cidx * dl + 3];
+    for (int t = threadIdx.x; t < e8; t += blockDim.x) {
+        size_t p = (size_t)cidx * e8 + t;
+        out[p] = t < ne ? eval[p] * dinv[need[(size_t)cidx * n4 + ecol[p]]] : 0.0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ apply
 struct TileDev {
-    const int* meta; const int* need_rows; const int* ent_ptr;
-    const unsigned short* ent_col; const double* ent_val; const unsigned short* self_slot;
-    // byte offsets of the shared-memory regions (after the staged input rows at offset 0)
-    unsigned off_bs, off_evals, off_dneed, off_drow, off_eptr, off_ecols, off_sself, off_red;
+    const int* desc; const int* need; const unsigned short* ecol; const double* eval;
+    int nchunks, R, dl, n4, e8;
+    // shared-memory geometry (bytes)
+    unsigned cb_bytes, st_bytes, off_bs, off_drow, off_red;
 };
 
-template <int VEC>
-__device__ __forceinline__ void ldv(const double* __restrict__ p, bool ok0, bool ok1, double& x0, double& x1) {
-    if (VEC == 2 && ok1) {
-        double2 v = *reinterpret_cast<const double2*>(p);
-        x0 = v.x; x1 = v.y;
-    } else if (ok0) {
-        x0 = p[0]; x1 = 0.0;
-    } else {
-        x0 = 0.0; x1 = 0.0;
-    }
-}
 template <int VEC>
 __device__ __forceinline__ void stv(double* __restrict__ p, bool ok0, bool ok1, double x0, double x1) {
     if (VEC == 2 && ok1) *reinterpret_cast<double2*>(p) = make_double2(x0, x1);
     else if (ok0) p[0] = x0;
 }
-// asynchronous global -> shared copy of this lane's VEC columns of one row (zero fill past column k)
+// asynchronous global -> shared copy of this lane's VEC columns of one row (`bytes` valid, zero fill beyond)
 template <int VEC>
-__device__ __forceinline__ void cp_row(double* smem_dst, const double* __restrict__ src, bool ok0, bool ok1) {
+__device__ __forceinline__ void cp_row(unsigned smem_addr, const double* __restrict__ src, int bytes) {
+    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(src), "r"(bytes));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_addr), "l"(src), "r"(bytes));
+}
+__device__ __forceinline__ void cp16(void* smem_dst, const void* __restrict__ src) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (VEC == 2) {
-        int bytes = ok1 ? 16 : (ok0 ? 8 : 0);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(src), "r"(bytes));
-    } else {
-        int bytes = ok0 ? 8 : 0;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(src), "r"(bytes));
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
+}
+__device__ __forceinline__ void cp8(void* smem_dst, const void* __restrict__ src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
 }
 
 // CW lanes share one row (each owning VEC adjacent columns); a warp instruction covers 32 / CW rows.
-// Phase 1: every input the chunk needs -- the staged rows of X, the chunk's own rows of B (or of Y for TM_MULT_ADD),
-// its matrix entries and smoother scalings -- is requested up front (cp.async, no register round trips), so a CTA has
-// its whole working set in flight at once.  Phase 2 works from shared memory only and streams the result rows out.
+// Work items of a CTA: for each column slab, its chunks blockIdx.x + j * gridDim.x  (slab-major, so the per-lane dot
+// accumulators run over all chunks of a slab and are reduced once per slab).
 template <int CW, int VEC, int MODE>
 __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    extern __shared__ __align__(16) unsigned char sm[];
     constexpr int SW = CW * VEC;
+    constexpr int SWB = SW * 8;
     constexpr int RPW = 32 / CW;
     constexpr bool HAS_B = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
     constexpr bool HAS_D = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
-    constexpr bool NEED_SELF = (MODE == TM_PMULT_DOT || MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
-    double* xs = reinterpret_cast<double*>(smraw);
-    double* bs = reinterpret_cast<double*>(smraw + op.off_bs);
-    double* evals = reinterpret_cast<double*>(smraw + op.off_evals);
-    double* dneed = reinterpret_cast<double*>(smraw + op.off_dneed);
-    double* drow = reinterpret_cast<double*>(smraw + op.off_drow);
-    int* eptr = reinterpret_cast<int*>(smraw + op.off_eptr);
-    unsigned short* ecols = reinterpret_cast<unsigned short*>(smraw + op.off_ecols);
-    unsigned short* sself = reinterpret_cast<unsigned short*>(smraw + op.off_sself);
-    double (*red)[64] = reinterpret_cast<double (*)[64]>(smraw + op.off_red);
+    constexpr bool NEED_SELF = (MODE == TM_MULT_DOT || MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
+    constexpr bool HAS_DOT = (MODE == TM_MULT_DOT || MODE == TM_JACOBI_DOT);
+    unsigned char* cb0 = sm;                               // 4 chunk-record buffers
+    unsigned char* st0 = sm + 4 * (size_t)op.cb_bytes;     // 2 stage buffers (staged rows, rhs rows, scalings)
+    double (*red)[64] = reinterpret_cast<double (*)[64]>(sm + op.off_red);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int sub = lane / CW, cl = lane % CW;
-    // slab index fastest: CTAs dispatched together cover all column slabs of the same rows (whole DRAM pages)
-    const int nslab = (a.k + SW - 1) / SW;
-    const int slab = blockIdx.x % nslab, cidx = blockIdx.x / nslab;
-    const int col = slab * SW + cl * VEC;
-    const bool ok0 = col < a.k, ok1 = (VEC == 2) && (col + 1 < a.k);
-    const int4 m0 = reinterpret_cast<const int4*>(op.meta)[2 * cidx], m1 = reinterpret_cast<const int4*>(op.meta)[2 * cidx + 1];
-    const int r0 = m0.x, nr = m0.y, r1 = r0 + nr, n0 = m0.z, nneed = m0.w, e0 = m1.x, ne = m1.y, own = m1.z;
+    const int wsub = warp * RPW + sub;
     const int sstride = nwarps * RPW;
+    const int nslab = (a.k + SW - 1) / SW;
+    const int nmine = ((int)op.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int T = nmine * nslab;
+    const unsigned st_base = (unsigned)__cvta_generic_to_shared(st0) + cl * VEC * 8;
 
-    // ---- phase 1a: staged input rows
-    if (MODE == TM_PMULT_DOT) {
-        // p_j = z_j + beta p_j needs two inputs per row: through registers, 8 rows in flight per lane group
-        constexpr int U = 8;
-        double beta0 = ok0 ? a.beta[col] : 0.0, beta1 = ok1 ? a.beta[col + 1] : 0.0;
-        for (int s = warp * RPW + sub; s < nneed; s += sstride * U) {
-            int rows[U];
-            double v0[U], v1[U], w0[U], w1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int ss = s + u * sstride;
-                rows[u] = ss < nneed ? op.need_rows[n0 + ss] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v0[u] = v1[u] = w0[u] = w1[u] = 0.0;
-                if (rows[u] >= 0) {
-                    ldv<VEC>(a.X + (int64_t)rows[u] * a.ldx + col, ok0, ok1, v0[u], v1[u]);
-                    ldv<VEC>(a.Pin + (int64_t)rows[u] * a.ldp + col, ok0, ok1, w0[u], w1[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (rows[u] < 0) continue;
-                int ss = s + u * sstride;
-                double x0 = fma(beta0, w0[u], v0[u]), x1 = fma(beta1, w1[u], v1[u]);
-                if (rows[u] >= r0 && rows[u] < r1) stv<VEC>(a.Pout + (int64_t)rows[u] * a.ldp + col, ok0, ok1, x0, x1);
-                if (VEC == 2) *reinterpret_cast<double2*>(xs + (size_t)ss * SW + cl * 2) = make_double2(x0, x1);
-                else xs[(size_t)ss * SW + cl] = x0;
-            }
+    auto issue_record = [&](int t) {
+        if (t >= T) return;
+        const int j = t % nmine;
+        const size_t cidx = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+        unsigned char* dst = cb0 + (size_t)(t & 3) * op.cb_bytes;
+        const int4* s0 = reinterpret_cast<const int4*>(op.desc + cidx * op.dl);
+        const int4* s1 = reinterpret_cast<const int4*>(op.need + cidx * op.n4);
+        const int4* s2 = reinterpret_cast<const int4*>(op.ecol + cidx * op.e8);
+        const int4* s3 = reinterpret_cast<const int4*>(op.eval + cidx * op.e8);
+        const int n0 = op.dl >> 2, n1 = op.n4 >> 2, n2 = op.e8 >> 3, n3 = op.e8 >> 1;
+        int4* d = reinterpret_cast<int4*>(dst);
+        for (int i = tid; i < n0; i += blockDim.x) cp16(d + i, s0 + i);
+        d += n0;
+        for (int i = tid; i < n1; i += blockDim.x) cp16(d + i, s1 + i);
+        d += n1;
+        for (int i = tid; i < n2; i += blockDim.x) cp16(d + i, s2 + i);
+        d += n2;
+        for (int i = tid; i < n3; i += blockDim.x) cp16(d + i, s3 + i);
+    };
+    auto issue_item = [&](int t) {
+        if (t >= T) return;
+        const int slab = t / nmine;
+        const int* dsc = reinterpret_cast<const int*>(cb0 + (size_t)(t & 3) * op.cb_bytes);
+        const int* need = dsc + op.dl;
+        const int r0 = dsc[0], nr = dsc[1], nneed = dsc[2], own = dsc[4], nown = dsc[5];
+        const unsigned xs_a = st_base + (unsigned)(t & 1) * op.st_bytes;
+        const int col = slab * SW + cl * VEC;
+        const int bytes = (VEC == 2) ? (col + 1 < a.k ? 16 : (col < a.k ? 8 : 0)) : (col < a.k ? 8 : 0);
+        const double* Xc = a.X + col;
+        const int64_t ldx = a.ldx;
+        // own rows sit in consecutive slots [own, own + nown): no list lookup
+        for (int r = wsub; r < nown; r += sstride) cp_row<VEC>(xs_a + (unsigned)(own + r) * SWB, Xc + (int64_t)(r0 + r) * ldx, bytes);
+        for (int ss = wsub; ss < own; ss += sstride) cp_row<VEC>(xs_a + (unsigned)ss * SWB, Xc + (int64_t)need[ss] * ldx, bytes);
+        for (int ss = own + nown + wsub; ss < nneed; ss += sstride) cp_row<VEC>(xs_a + (unsigned)ss * SWB, Xc + (int64_t)need[ss] * ldx, bytes);
+        if (HAS_B) {
+            const unsigned bs_a = xs_a + op.off_bs;
+            const double* Bc = ((MODE == TM_MULT_ADD) ? a.Y : a.B) + col;
+            const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
+            for (int r = wsub; r < nr; r += sstride) cp_row<VEC>(bs_a + (unsigned)r * SWB, Bc + (int64_t)(r0 + r) * lds, bytes);
         }
-    } else {
-        // own rows sit in consecutive slots [own, own + nr): no index lookup, requested first
-        if (own >= 0)
-            for (int r = warp * RPW + sub; r < nr; r += sstride)
-                cp_row<VEC>(xs + (size_t)(own + r) * SW + cl * VEC, a.X + (int64_t)(r0 + r) * a.ldx + col, ok0, ok1);
-        constexpr int U = 8;
-        const int nhalo = own >= 0 ? nneed - nr : nneed;
-        for (int s = warp * RPW + sub; s < nhalo; s += sstride * U) {
-            int rows[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int hh = s + u * sstride;
-                int ss = (own >= 0 && hh >= own) ? hh + nr : hh;
-                rows[u] = hh < nhalo ? op.need_rows[n0 + ss] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (rows[u] < 0) continue;
-                int hh = s + u * sstride;
-                int ss = (own >= 0 && hh >= own) ? hh + nr : hh;
-                cp_row<VEC>(xs + (size_t)ss * SW + cl * VEC, a.X + (int64_t)rows[u] * a.ldx + col, ok0, ok1);
-            }
+        if (HAS_D) {
+            double* drow = reinterpret_cast<double*>(st0 + (size_t)(t & 1) * op.st_bytes + op.off_drow);
+            for (int r = tid; r < nr; r += blockDim.x) cp8(drow + r, a.dinv + r0 + r);
         }
-        if (MODE == TM_PRESMOOTH2)
-            for (int t = tid; t < nneed; t += blockDim.x) dneed[t] = a.dinv[op.need_rows[n0 + t]];
-    }
-    // ---- phase 1b: own rows of the right-hand side (or of Y when accumulating)
-    if (HAS_B) {
-        const double* src = (MODE == TM_MULT_ADD) ? a.Y : a.B;
-        const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
-        for (int r = warp * RPW + sub; r < nr; r += sstride)
-            cp_row<VEC>(bs + (size_t)r * SW + cl * VEC, src + (int64_t)(r0 + r) * lds + col, ok0, ok1);
-    }
+    };
+
+    // ---- prologue: the first three chunk records, then the first work item in flight
+    issue_record(0);
+    issue_record(1);
+    issue_record(2);
     asm volatile("cp.async.commit_group;\n" ::);
-    // ---- phase 1c: matrix entries, row pointers, scalings
-    for (int t = tid; t < ne; t += blockDim.x) {
-        evals[t] = op.ent_val[e0 + t];
-        ecols[t] = op.ent_col[e0 + t];
-    }
-    for (int t = tid; t <= nr; t += blockDim.x) eptr[t] = op.ent_ptr[r0 + t] - e0;
-    if (NEED_SELF)
-        for (int t = tid; t < nr; t += blockDim.x) sself[t] = op.self_slot[r0 + t];
-    if (HAS_D)
-        for (int t = tid; t < nr; t += blockDim.x) drow[t] = a.dinv[r0 + t];
     asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
-    if (MODE == TM_PRESMOOTH2) {
-        // the staged rows hold b_j; fold the first sweep s_j = d_j b_j into the matrix entries: a_ij d_j
-        for (int t = tid; t < ne; t += blockDim.x) evals[t] *= dneed[ecols[t]];
-        __syncthreads();
-    }
+    issue_item(0);
+    asm volatile("cp.async.commit_group;\n" ::);
 
-    // ---- phase 2: rows, from shared memory only
     double d0 = 0.0, d1 = 0.0;
-    for (int r = warp * RPW + sub; r < nr; r += sstride) {
-        const int64_t row = r0 + r;
-        const int ea = eptr[r], eb = eptr[r + 1];
-        double acc0 = 0.0, acc1 = 0.0;
-        int e = ea;
-        for (; e + 4 <= eb; e += 4) {
-            double x[4][2];
-            double v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                v[q] = evals[e + q];
-                const double* xp = xs + (size_t)ecols[e + q] * SW + cl * VEC;
-                if (VEC == 2) { double2 t2 = *reinterpret_cast<const double2*>(xp); x[q][0] = t2.x; x[q][1] = t2.y; }
-                else { x[q][0] = xp[0]; x[q][1] = 0.0; }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { acc0 = fma(v[q], x[q][0], acc0); if (VEC == 2) acc1 = fma(v[q], x[q][1], acc1); }
-        }
-        for (; e < eb; ++e) {
-            double v = evals[e];
-            const double* xp = xs + (size_t)ecols[e] * SW + cl * VEC;
-            if (VEC == 2) { double2 t2 = *reinterpret_cast<const double2*>(xp); acc0 = fma(v, t2.x, acc0); acc1 = fma(v, t2.y, acc1); }
-            else acc0 = fma(v, xp[0], acc0);
-        }
-        double s0 = 0.0, s1 = 0.0;
-        if (NEED_SELF) {
-            unsigned short sl = sself[r];
-            if (sl != 0xffff) {
-                const double* xp = xs + (size_t)sl * SW + cl * VEC;
-                s0 = xp[0];
-                if (VEC == 2) s1 = xp[1];
-            }
-        }
-        double b0 = 0.0, b1 = 0.0;
-        if (HAS_B) {
-            const double* bp = bs + (size_t)r * SW + cl * VEC;
-            b0 = bp[0];
-            if (VEC == 2) b1 = bp[1];
-        }
-        double y0, y1;
-        if (MODE == TM_MULT) { y0 = acc0; y1 = acc1; }
-        else if (MODE == TM_MULT_ADD) { y0 = b0 + acc0; y1 = b1 + acc1; }
-        else if (MODE == TM_PMULT_DOT) { y0 = acc0; y1 = acc1; d0 = fma(s0, acc0, d0); d1 = fma(s1, acc1, d1); }
-        else if (MODE == TM_RESID) { y0 = b0 - acc0; y1 = b1 - acc1; }
-        else if (MODE == TM_PRESMOOTH2) {
-            // s0 = b_i (raw), acc = sum_j a_ij d_j b_j:  y = d_i b_i + d_i (b_i - acc)
-            double di = drow[r];
-            y0 = di * (2.0 * s0 - acc0); y1 = di * (2.0 * s1 - acc1);
-        } else {   // Jacobi
-            double di = drow[r];
-            y0 = fma(di, b0 - acc0, s0); y1 = fma(di, b1 - acc1, s1);
-            if (MODE == TM_JACOBI_DOT) { d0 = fma(b0, y0, d0); d1 = fma(b1, y1, d1); }
-        }
-        stv<VEC>(a.Y + row * a.ldy + col, ok0, ok1, y0, y1);
-    }
-    if (MODE == TM_PMULT_DOT || MODE == TM_JACOBI_DOT) {
-        red[warp][lane * VEC] = d0;
-        if (VEC == 2) red[warp][lane * VEC + 1] = d1;
+    for (int t = 0; t < T; ++t) {
+        // requests of the next work item and the chunk record three items ahead (its buffer was last read by item t-1)
+        issue_item(t + 1);
+        issue_record(t + 3);
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 1;\n" ::);
         __syncthreads();
-        if (tid < SW) {
-            int ccl = tid / VEC, v = tid % VEC;
+
+        const int slab = t / nmine;
+        const unsigned char* cb = cb0 + (size_t)(t & 3) * op.cb_bytes;
+        const int* dsc = reinterpret_cast<const int*>(cb);
+        const int r0 = dsc[0], nr = dsc[1], W = dsc[3];
+        const unsigned short* sself = reinterpret_cast<const unsigned short*>(dsc + 8);
+        const unsigned short* ecols = reinterpret_cast<const unsigned short*>(dsc + op.dl + op.n4);
+        const double* evals = reinterpret_cast<const double*>(cb + (size_t)(op.dl + op.n4) * 4 + (size_t)op.e8 * 2);
+        const unsigned char* st = st0 + (size_t)(t & 1) * op.st_bytes;
+        const double* xs = reinterpret_cast<const double*>(st) + cl * VEC;
+        const double* bs = reinterpret_cast<const double*>(st + op.off_bs) + cl * VEC;
+        const double* drow = reinterpret_cast<const double*>(st + op.off_drow);
+        const int col = slab * SW + cl * VEC;
+        const bool ok0 = col < a.k, ok1 = (VEC == 2) && (col + 1 < a.k);
+        double* Yc = a.Y + col;
+
+        for (int r = wsub; r < nr; r += sstride) {
+            const unsigned short* ec = ecols + r * W;
+            const double* ev = evals + r * W;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int w = 0; w < W; w += 2) {
+                const unsigned cc = *reinterpret_cast<const unsigned*>(ec + w);
+                const double2 vv = *reinterpret_cast<const double2*>(ev + w);
+                const double* xa = xs + (cc & 0xffffu) * SW;
+                const double* xb = xs + (cc >> 16) * SW;
+                if (VEC == 2) {
+                    const double2 ta = *reinterpret_cast<const double2*>(xa), tb = *reinterpret_cast<const double2*>(xb);
+                    acc0 = fma(vv.x, ta.x, acc0); acc1 = fma(vv.x, ta.y, acc1);
+                    acc0 = fma(vv.y, tb.x, acc0); acc1 = fma(vv.y, tb.y, acc1);
+                } else {
+                    acc0 = fma(vv.x, xa[0], acc0);
+                    acc0 = fma(vv.y, xb[0], acc0);
+                }
+            }
+            double s0 = 0.0, s1 = 0.0;
+            if (NEED_SELF) {
+                const unsigned sl = sself[r];
+                if (sl != 0xffffu) {
+                    const double* xp = xs + sl * SW;
+                    s0 = xp[0];
+                    if (VEC == 2) s1 = xp[1];
+                }
+            }
+            double b0 = 0.0, b1 = 0.0;
+            if (HAS_B) {
+                const double* bp = bs + r * SW;
+                b0 = bp[0];
+                if (VEC == 2) b1 = bp[1];
+            }
+            double y0, y1;
+            if (MODE == TM_MULT) { y0 = acc0; y1 = acc1; }
+            else if (MODE == TM_MULT_ADD) { y0 = b0 + acc0; y1 = b1 + acc1; }
+            else if (MODE == TM_MULT_DOT) { y0 = acc0; y1 = acc1; d0 = fma(s0, acc0, d0); d1 = fma(s1, acc1, d1); }
+            else if (MODE == TM_RESID) { y0 = b0 - acc0; y1 = b1 - acc1; }
+            else if (MODE == TM_PRESMOOTH2) {
+                // s = b_i, acc = sum_j (a_ij d_j) b_j:  y = d_i b_i + d_i (b_i - acc)
+                const double di = drow[r];
+                y0 = di * (2.0 * s0 - acc0); y1 = di * (2.0 * s1 - acc1);
+            } else {   // Jacobi
+                const double di = drow[r];
+                y0 = fma(di, b0 - acc0, s0); y1 = fma(di, b1 - acc1, s1);
+                if (MODE == TM_JACOBI_DOT) { d0 = fma(b0, y0, d0); d1 = fma(b1, y1, d1); }
+            }
+            stv<VEC>(Yc + (int64_t)(r0 + r) * a.ldy, ok0, ok1, y0, y1);
+        }
+        const bool slab_done = HAS_DOT && ((t + 1) % nmine == 0);
+        if (slab_done) {
+            red[warp][lane * VEC] = d0;
+            if (VEC == 2) red[warp][lane * VEC + 1] = d1;
+            d0 = d1 = 0.0;
+        }
+        __syncthreads();
+        if (slab_done && tid < SW) {
+            const int ccl = tid / VEC, v = tid % VEC;
             double s = 0.0;
             for (int w = 0; w < nwarps; ++w)
                 for (int sb = 0; sb < RPW; ++sb) s += red[w][(sb * CW + ccl) * VEC + v];
-            int cc = slab * SW + tid;
-            if (cc < a.k) a.partials[(int64_t)cidx * a.k + cc] = s;
+            const int cc = slab * SW + tid;
+            if (cc < a.k) a.partials[(size_t)blockIdx.x * a.k + cc] = s;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+// Fallback for operators whose chunk working set does not fit in shared memory (e.g. wide 3-D transfer operators):
+// same format, rows gathered straight from global memory (warp per row, lanes across 32 columns, slabs looped).
+template <int MODE>
+__global__ void __launch_bounds__(256) tileop_direct_kernel(TileDev op, TileArgs a) {
+    constexpr bool HAS_B = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
+    constexpr bool HAS_D = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
+    constexpr bool NEED_SELF = (MODE == TM_MULT_DOT || MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
+    constexpr bool HAS_DOT = (MODE == TM_MULT_DOT || MODE == TM_JACOBI_DOT);
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nslab = (a.k + 31) / 32;
+    for (int slab = 0; slab < nslab; ++slab) {
+        const int col = slab * 32 + lane;
+        const bool ok = col < a.k;
+        double d0 = 0.0;
+        for (int cidx = blockIdx.x; cidx < op.nchunks; cidx += gridDim.x) {
+            const int* dsc = op.desc + (size_t)cidx * op.dl;
+            const int* need = op.need + (size_t)cidx * op.n4;
+            const unsigned short* ecols = op.ecol + (size_t)cidx * op.e8;
+            const double* evals = op.eval + (size_t)cidx * op.e8;
+            const unsigned short* sself = reinterpret_cast<const unsigned short*>(dsc + 8);
+            const int r0 = dsc[0], nr = dsc[1], W = dsc[3];
+            for (int r = warp; r < nr; r += 8) {
+                double acc = 0.0;
+                for (int w = 0; w < W; ++w) {
+                    double v = evals[r * W + w];
+                    if (v != 0.0 && ok) acc = fma(v, a.X[(int64_t)need[ecols[r * W + w]] * a.ldx + col], acc);
+                }
+                double s0 = 0.0, b0 = 0.0, di = 0.0;
+                const int64_t row = r0 + r;
+                if (NEED_SELF && sself[r] != 0xffff && ok) s0 = a.X[(int64_t)need[sself[r]] * a.ldx + col];
+                if (HAS_B && ok) b0 = (MODE == TM_MULT_ADD) ? a.Y[row * a.ldy + col] : a.B[row * a.ldb + col];
+                if (HAS_D) di = a.dinv[row];
+                double y;
+                if (MODE == TM_MULT) y = acc;
+                else if (MODE == TM_MULT_ADD) y = b0 + acc;
+                else if (MODE == TM_MULT_DOT) { y = acc; d0 = fma(s0, acc, d0); }
+                else if (MODE == TM_RESID) y = b0 - acc;
+                else if (MODE == TM_PRESMOOTH2) y = di * (2.0 * s0 - acc);
+                else { y = fma(di, b0 - acc, s0); if (MODE == TM_JACOBI_DOT) d0 = fma(b0, y, d0); }
+                if (ok) a.Y[row * a.ldy + col] = y;
+            }
+        }
+        if (HAS_DOT) {
+            red[warp][lane] = d0;
+            __syncthreads();
+            if (warp == 0 && ok) {
+                double s = 0.0;
+                for (int w = 0; w < 8; ++w) s += red[w][lane];
+                a.partials[(size_t)blockIdx.x * a.k + col] = s;
+            }
+            __syncthreads();
         }
     }
 }
 
 inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// shared-memory layout for one (operator, mode, slab width); returns the total and fills the offsets
+// shared-memory geometry for one (operator, mode, slab width); returns the total bytes
 size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d) {
     bool has_b = (mode == TM_JACOBI || mode == TM_JACOBI_DOT || mode == TM_RESID || mode == TM_MULT_ADD);
-    size_t off = al16((size_t)op.max_need * SW * sizeof(double));
-    unsigned o_bs = (unsigned)off;
-    if (has_b) off += al16((size_t)op.max_rows * SW * sizeof(double));
-    unsigned o_ev = (unsigned)off; off += al16((size_t)op.max_ent * sizeof(double));
-    unsigned o_dn = (unsigned)off;
-    if (mode == TM_PRESMOOTH2) off += al16((size_t)op.max_need * sizeof(double));
-    unsigned o_dr = (unsigned)off; off += al16((size_t)op.max_rows * sizeof(double));
-    unsigned o_ep = (unsigned)off; off += al16((size_t)(op.max_rows + 1) * sizeof(int));
-    unsigned o_ec = (unsigned)off; off += al16((size_t)op.max_ent * sizeof(unsigned short));
-    unsigned o_ss = (unsigned)off; off += al16((size_t)op.max_rows * sizeof(unsigned short));
-    unsigned o_red = (unsigned)off;
-    if (mode == TM_PMULT_DOT || mode == TM_JACOBI_DOT) off += 16 * 64 * sizeof(double);
-    if (d) d->off_red = o_red;
-    if (d) { d->off_bs = o_bs; d->off_evals = o_ev; d->off_dneed = o_dn; d->off_drow = o_dr; d->off_eptr = o_ep; d->off_ecols = o_ec; d->off_sself = o_ss; }
-    return off;
+    bool has_d = (mode == TM_JACOBI || mode == TM_JACOBI_DOT || mode == TM_PRESMOOTH2);
+    bool has_dot = (mode == TM_MULT_DOT || mode == TM_JACOBI_DOT);
+    size_t cb = (size_t)op.dl * 4 + (size_t)op.n4 * 4 + (size_t)op.e8 * 2 + (size_t)op.e8 * 8;
+    size_t st = al16((size_t)op.max_need * SW * sizeof(double));
+    size_t o_bs = st;
+    if (has_b) st += al16((size_t)op.max_rows * SW * sizeof(double));
+    size_t o_dr = st;
+    if (has_d) st += al16((size_t)op.max_rows * sizeof(double));
+    size_t tot = 4 * cb + 2 * st;
+    size_t o_red = tot;
+    if (has_dot) tot += 16 * 64 * sizeof(double);
+    if (d) { d->cb_bytes = (unsigned)cb; d->st_bytes = (unsigned)st; d->off_bs = (unsigned)o_bs; d->off_drow = (unsigned)o_dr; d->off_red = (unsigned)o_red; }
+    return tot;
 }
 
-constexpr size_t SMEM_STATIC = 1024;                    // per-CTA reservation
-constexpr size_t SMEM_CAP = 227 * 1024 - SMEM_STATIC;   // per-CTA dynamic limit
+constexpr size_t SMEM_RESERVED = 1024;                    // per-CTA reservation of the hardware
+constexpr size_t SMEM_CAP = 227 * 1024 - SMEM_RESERVED;   // per-CTA dynamic limit
 
 template <int CW, int VEC, int MODE>
-int launch_variant(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a) {
+int launch_variant(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int* nparts) {
     constexpr int SW = CW * VEC;
     size_t smem = tile_layout(op, MODE, SW, &d);
     if (smem > SMEM_CAP) return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: chunk working set (%zu bytes) exceeds shared memory", smem);
@@ -392,33 +449,42 @@ int launch_variant(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a) 
         cudaFuncSetAttribute(tileop_kernel<CW, VEC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         attr_set = true;
     }
-    // two (or more) CTAs of 8 warps per SM when the working set allows it, otherwise one CTA of 16 warps
-    int threads = (2 * (smem + SMEM_STATIC) <= 227 * 1024) ? 256 : 512;
-    unsigned grid = (unsigned)op.nchunks * (unsigned)((a.k + SW - 1) / SW);
+    // persistent grid: as many CTAs as fit on the machine (8 warps each; one 16-warp CTA per SM if only one fits)
+    int per_sm = (int)((227 * 1024) / (smem + SMEM_RESERVED));
+    int threads = 256;
+    if (per_sm < 2) { per_sm = 1; threads = 512; }
+    if (per_sm > TILE_MAX_CTAS_PER_SM) per_sm = TILE_MAX_CTAS_PER_SM;
+    int64_t items = (int64_t)op.nchunks;
+    int grid = (int)(items < (int64_t)per_sm * SFEM_NUM_SMS ? items : (int64_t)per_sm * SFEM_NUM_SMS);
+    if (nparts) *nparts = grid;
     tileop_kernel<CW, VEC, MODE><<<grid, threads, smem, c->stream>>>(d, a);
     KCHECK(c);
     return SFEM_OK;
 }
 
 template <int MODE>
-int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs& a) {
+int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs& a, int* nparts) {
     bool al2 = (a.ldx % 2 == 0) && (a.ldy % 2 == 0) && (reinterpret_cast<uintptr_t>(a.X) % 16 == 0) &&
                (reinterpret_cast<uintptr_t>(a.Y) % 16 == 0) &&
-               (a.B == nullptr || (a.ldb % 2 == 0 && reinterpret_cast<uintptr_t>(a.B) % 16 == 0)) &&
-               (a.Pin == nullptr || (a.ldp % 2 == 0 && reinterpret_cast<uintptr_t>(a.Pin) % 16 == 0 &&
-                                     reinterpret_cast<uintptr_t>(a.Pout) % 16 == 0));
-    if (a.k <= 4) return launch_variant<4, 1, MODE>(c, op, d, a);
-    if (a.k <= 16) return launch_variant<16, 1, MODE>(c, op, d, a);
-    if (a.k > 32 && al2 && c->tile_sw != 32 && 2 * (tile_layout(op, MODE, 64, nullptr) + SMEM_STATIC) <= 227 * 1024) return launch_variant<32, 2, MODE>(c, op, d, a);
-    if (tile_layout(op, MODE, 32, nullptr) <= SMEM_CAP) return launch_variant<32, 1, MODE>(c, op, d, a);
-    return launch_variant<16, 1, MODE>(c, op, d, a);
+               (a.B == nullptr || (a.ldb % 2 == 0 && reinterpret_cast<uintptr_t>(a.B) % 16 == 0));
+    if (a.k <= 4 && tile_layout(op, MODE, 4, nullptr) <= SMEM_CAP) return launch_variant<4, 1, MODE>(c, op, d, a, nparts);
+    if (a.k <= 16 && tile_layout(op, MODE, 16, nullptr) <= SMEM_CAP) return launch_variant<16, 1, MODE>(c, op, d, a, nparts);
+    if (a.k > 32 && al2 && c->tile_sw != 32 && 2 * (tile_layout(op, MODE, 64, nullptr) + SMEM_RESERVED) <= 227 * 1024) return launch_variant<32, 2, MODE>(c, op, d, a, nparts);
+    if (tile_layout(op, MODE, 32, nullptr) <= SMEM_CAP) return launch_variant<32, 1, MODE>(c, op, d, a, nparts);
+    if (tile_layout(op, MODE, 16, nullptr) <= SMEM_CAP) return launch_variant<16, 1, MODE>(c, op, d, a, nparts);
+    // working set too large for shared memory: gather from global memory
+    int grid = op.nchunks < 4 * SFEM_NUM_SMS ? op.nchunks : 4 * SFEM_NUM_SMS;
+    if (nparts) *nparts = grid;
+    tileop_direct_kernel<MODE><<<grid, 256, 0, c->stream>>>(d, a);
+    KCHECK(c);
+    return SFEM_OK;
 }
 
 }  // namespace
 
 void tileop_free(TileOp* op) {
     if (!op) return;
-    void* ptrs[] = {op->chunk_ptr, op->need_ptr, op->need_rows, op->ent_ptr, op->ent_col, op->ent_val, op->self_slot, op->meta};
+    void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *op = TileOp();
@@ -431,65 +497,78 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
     op.nrows = nrows; op.ncols = ncols; op.nchunks = nchunks; op.max_rows = max_rows;
     int64_t nnz = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&nnz, ptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (nnz >= ((int64_t)1 << 31)) return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: more than 2^31 entries");
-    op.nnz = nnz;
-    CUDA_TRY(c, cudaMalloc(&op.chunk_ptr, sizeof(int) * ((size_t)nchunks + 1)));
-    CUDA_TRY(c, cudaMemcpyAsync(op.chunk_ptr, chunk_ptr, sizeof(int) * ((size_t)nchunks + 1), cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_TRY(c, cudaMalloc(&op.need_ptr, sizeof(int) * ((size_t)nchunks + 1)));
-    int *need_cnt = nullptr, *sums = nullptr, *stats = nullptr;
-    CUDA_TRY(c, cudaMalloc(&need_cnt, sizeof(int) * ((size_t)nchunks + 1)));
-    CUDA_TRY(c, cudaMalloc(&sums, sizeof(int) * ((size_t)nchunks / 1024 + 8)));
+    int* stats = nullptr;
     CUDA_TRY(c, cudaMalloc(&stats, sizeof(int) * 4));
     CUDA_TRY(c, cudaMemsetAsync(stats, 0, sizeof(int) * 4, c->stream));
-    int rc = SFEM_OK;
-    {
-        ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
+    static bool attr_set = false;
+    if (!attr_set) {
         cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TB_MAXENT * sizeof(int)));
         cudaFuncSetAttribute(tile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TB_MAXENT * sizeof(int)));
-        tile_count_kernel<<<nchunks, TB_THREADS, 2 * TB_MAXENT * sizeof(int), c->stream>>>(op.chunk_ptr, ptr, idx, need_cnt, stats);
-        c->launches++;
-        rc = exclusive_scan<int>(c, need_cnt, nchunks, op.need_ptr, sums);
+        attr_set = true;
     }
-    int hstats[4] = {0, 0, 0, 0};
-    int total_need = 0;
-    if (rc == SFEM_OK) {
-        cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(&total_need, op.need_ptr + nchunks, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = sfem_fail(c, SFEM_ERR_CUDA, "tileop: count pass failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    cudaFree(need_cnt); cudaFree(sums); cudaFree(stats);
-    if (rc) { tileop_free(&op); return rc; }
-    if (hstats[2]) { tileop_free(&op); return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: a chunk has too many entries or columns"); }
-    op.max_need = hstats[0]; op.max_ent = hstats[1];
-    CUDA_TRY(c, cudaMalloc(&op.need_rows, sizeof(int) * (size_t)(total_need > 0 ? total_need : 1)));
-    CUDA_TRY(c, cudaMalloc(&op.ent_ptr, sizeof(int) * ((size_t)nrows + 1)));
-    CUDA_TRY(c, cudaMalloc(&op.ent_col, sizeof(unsigned short) * (size_t)(nnz > 0 ? nnz : 1)));
-    CUDA_TRY(c, cudaMalloc(&op.ent_val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)));
-    CUDA_TRY(c, cudaMalloc(&op.self_slot, sizeof(unsigned short) * (size_t)nrows));
-    CUDA_TRY(c, cudaMalloc(&op.meta, sizeof(int) * 8 * (size_t)nchunks));
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
-        tile_fill_kernel<<<nchunks, TB_THREADS, 2 * TB_MAXENT * sizeof(int), c->stream>>>(nrows, nrows == ncols ? 1 : 0, op.chunk_ptr, ptr, idx, val, op.need_ptr,
-                                                                op.need_rows, op.ent_ptr, op.ent_col, op.ent_val, op.self_slot, op.meta);
+        tile_count_kernel<<<nchunks, TB_THREADS, 2 * TB_MAXENT * sizeof(int), c->stream>>>(chunk_ptr, ptr, idx, stats);
+        c->launches++;
+    }
+    int hstats[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(stats);
+    if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: count pass failed: %s", cudaGetErrorString(e));
+    if (hstats[2]) return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: a chunk has too many entries or columns");
+    op.nnz = nnz;
+    op.max_need = hstats[0] > 0 ? hstats[0] : 1;
+    op.max_ent = max_rows * (hstats[1] > 0 ? hstats[1] : 2);
+    op.dl = (8 + (max_rows + 1) / 2 + 3) & ~3;
+    op.n4 = (op.max_need + 3) & ~3;
+    op.e8 = (op.max_ent + 7) & ~7;
+    size_t nc = (size_t)nchunks;
+    CUDA_TRY(c, cudaMalloc(&op.desc, sizeof(int) * nc * op.dl));
+    CUDA_TRY(c, cudaMalloc(&op.need, sizeof(int) * nc * op.n4));
+    CUDA_TRY(c, cudaMalloc(&op.ecol, sizeof(unsigned short) * nc * op.e8));
+    CUDA_TRY(c, cudaMalloc(&op.eval, sizeof(double) * nc * op.e8));
+    CUDA_TRY(c, cudaMemsetAsync(op.desc, 0, sizeof(int) * nc * op.dl, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(op.need, 0, sizeof(int) * nc * op.n4, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(op.ecol, 0, sizeof(unsigned short) * nc * op.e8, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(op.eval, 0, sizeof(double) * nc * op.e8, c->stream));
+    {
+        ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
+        tile_fill_kernel<<<nchunks, TB_THREADS, 2 * TB_MAXENT * sizeof(int), c->stream>>>(nrows == ncols ? 1 : 0, max_rows, op.dl, op.n4, op.e8,
+                                                                                        chunk_ptr, ptr, idx, val, op.desc, op.need, op.ecol, op.eval);
         KCHECK(c);
     }
+    if (getenv("SFEM_DEBUG")) fprintf(stderr, "tileop %lld x %lld nnz %lld chunks %d R %d need %d W %d dl %d\n", (long long)nrows, (long long)ncols, (long long)nnz, nchunks, max_rows, op.max_need, hstats[1], op.dl);
     *out = op;
     return SFEM_OK;
 }
 
-int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArgs& a, double bytes) {
+int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv) {
+    if (op->nchunks <= 0) return SFEM_OK;
+    if (!op->eval_scaled) CUDA_TRY(c, cudaMalloc(&op->eval_scaled, sizeof(double) * (size_t)op->nchunks * op->e8));
+    ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
+    tile_scale_kernel<<<op->nchunks, 128, 0, c->stream>>>(op->nchunks, op->dl, op->n4, op->e8, op->desc, op->need, op->ecol, op->eval, dinv, op->eval_scaled);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
+int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArgs& a, double bytes, int* nparts) {
+    if (nparts) *nparts = 0;
     if (op.nrows <= 0 || a.k <= 0) return SFEM_OK;
-    TileDev d{op.meta, op.need_rows, op.ent_ptr, op.ent_col, op.ent_val, op.self_slot, 0, 0, 0, 0, 0, 0, 0, 0};
+    TileDev d;
+    d.desc = op.desc; d.need = op.need; d.ecol = op.ecol;
+    d.eval = (mode == TM_PRESMOOTH2) ? op.eval_scaled : op.eval;
+    if (!d.eval) return sfem_fail(c, SFEM_ERR_STATE, "tileop_apply: scaled entries not built");
+    d.nchunks = op.nchunks; d.R = op.max_rows; d.dl = op.dl; d.n4 = op.n4; d.e8 = op.e8;
     ProfScope ps(c, tag, bytes, 2.0 * (double)op.nnz * a.k);
     switch (mode) {
-        case TM_MULT: return launch_mode<TM_MULT>(c, op, d, a);
-        case TM_MULT_ADD: return launch_mode<TM_MULT_ADD>(c, op, d, a);
-        case TM_PMULT_DOT: return launch_mode<TM_PMULT_DOT>(c, op, d, a);
-        case TM_JACOBI: return launch_mode<TM_JACOBI>(c, op, d, a);
-        case TM_JACOBI_DOT: return launch_mode<TM_JACOBI_DOT>(c, op, d, a);
-        case TM_RESID: return launch_mode<TM_RESID>(c, op, d, a);
-        case TM_PRESMOOTH2: return launch_mode<TM_PRESMOOTH2>(c, op, d, a);
+        case TM_MULT: return launch_mode<TM_MULT>(c, op, d, a, nparts);
+        case TM_MULT_ADD: return launch_mode<TM_MULT_ADD>(c, op, d, a, nparts);
+        case TM_MULT_DOT: return launch_mode<TM_MULT_DOT>(c, op, d, a, nparts);
+        case TM_JACOBI: return launch_mode<TM_JACOBI>(c, op, d, a, nparts);
+        case TM_JACOBI_DOT: return launch_mode<TM_JACOBI_DOT>(c, op, d, a, nparts);
+        case TM_RESID: return launch_mode<TM_RESID>(c, op, d, a, nparts);
+        case TM_PRESMOOTH2: return launch_mode<TM_PRESMOOTH2>(c, op, d, a, nparts);
     }
     return sfem_fail(c, SFEM_ERR_ARG, "tileop_apply: bad mode");
 }

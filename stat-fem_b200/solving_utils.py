@@ -18,18 +18,27 @@ _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_si
 
 
 def _lattice_nodes(coords):
-    "level-1 lattice: 2^p + 1 nodes per direction with a spacing of 1.5 to 3 mesh widths"
+    """level-1 lattice: 2^p cells per direction with a spacing of TWICE the estimated mesh width, anchored at the lower
+    corner of the bounding box and extended past the upper corner if necessary.  On lattice-like meshes every DOF then
+    sits on a lattice node, edge midpoint or cell centre, the transfer weights are exactly 0, 1/2, 1/4, 1, and all
+    Galerkin coarse operators stay compact (3^d points) instead of filling their 5^d stencils."""
     n, d = coords.shape
     lo, hi = coords.min(axis=0), coords.max(axis=0)
     ext = np.where(hi > lo, hi - lo, 1.)
     geo = float(np.prod(ext) ** (1. / d))
     per_side = float(n) ** (1. / d)
-    m1 = []
+    if abs(per_side - round(per_side)) < 1.e-6:
+        per_side = float(round(per_side))
+    m1, hi_lat = [], []
     for k in range(d):
-        cells = max(per_side * ext[k] / geo - 1., 2.)
-        p = max(int(np.floor(np.log2(cells / 1.5) + 1.e-9)), 1)      # lattice spacing in [1.5, 3) mesh widths
+        cells = max(per_side * ext[k] / geo - 1., 2.)          # estimated number of mesh cells along direction k
+        if abs(cells - round(cells)) < 1.e-6:
+            cells = float(round(cells))
+        H = 2. * ext[k] / cells
+        p = max(int(np.ceil(np.log2(ext[k] / H) - 1.e-9)), 1)
         m1.append(2 ** p + 1)
-    return lo, hi, m1
+        hi_lat.append(lo[k] + H * 2 ** p)
+    return lo, np.array(hi_lat), m1
 
 
 class SparseSolver(object):
