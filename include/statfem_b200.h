@@ -63,9 +63,12 @@ int sfem_profile_read(sfem_ctx* ctx, double* ms_out_host, double* bytes_out_host
 int sfem_set_stiffness(sfem_ctx* ctx, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals);
 /* Build the lattice multigrid preconditioner.  coords: n x dim row-major DOF coordinates; bc_mask: n bytes (1 =
  * Dirichlet DOF); lo/hi_host: bounding box; m1_host: level-1 lattice nodes per direction (2^p + 1 each);
- * nu: Jacobi sweeps before and after; omega: damping; max_coarse: coarsen until a level has at most this many nodes. */
+ * nu: Jacobi sweeps before and after; omega / omega2: weights of the odd / even sweeps (equal: damped Jacobi; the
+ * reciprocals of the degree-2 Chebyshev roots on [lmax/4, lmax]: polynomial smoothing; the post-smoother applies
+ * them in reverse order so that the cycle stays symmetric); max_coarse: coarsen until a level has at most this many
+ * nodes. */
 int sfem_mg_setup(sfem_ctx* ctx, int dim, const double* coords, const uint8_t* bc_mask, const double* lo_host,
-                  const double* hi_host, const int* m1_host, int nu, double omega, int max_coarse);
+                  const double* hi_host, const int* m1_host, int nu, double omega, double omega2, int max_coarse);
 int sfem_mg_num_levels(sfem_ctx* ctx);
 int64_t sfem_mg_level_size(sfem_ctx* ctx, int level);
 size_t sfem_solve_workspace_bytes(sfem_ctx* ctx, int k, int precond);

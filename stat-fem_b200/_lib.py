@@ -43,7 +43,7 @@ def load_library():
         "sfem_last_error": (C.c_char_p, [vp]),
         "sfem_launch_count": (C.c_longlong, [vp]),
         "sfem_set_stiffness": (i32, [vp, i64, vp, vp, vp]),
-        "sfem_mg_setup": (i32, [vp, i32, vp, vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(i32), i32, f64, i32]),
+        "sfem_mg_setup": (i32, [vp, i32, vp, vp, C.POINTER(f64), C.POINTER(f64), C.POINTER(i32), i32, f64, f64, i32]),
         "sfem_mg_num_levels": (i32, [vp]),
         "sfem_mg_level_size": (i64, [vp, i32]),
         "sfem_solve_workspace_bytes": (sz, [vp, i32, i32]),

@@ -104,8 +104,10 @@ int sfem_set_stiffness(sfem_ctx* c, int64_t n, const int64_t* indptr, const int3
 }
 
 int sfem_mg_setup(sfem_ctx* c, int dim, const double* coords, const uint8_t* bc_mask, const double* lo_host,
-                  const double* hi_host, const int* m1_host, int nu, double omega, int max_coarse) {
+                  const double* hi_host, const int* m1_host, int nu, double omega, double omega2, int max_coarse) {
     GUARD(c);
+    if (!(omega > 0.0) || !(omega2 > 0.0)) return sfem_fail(c, SFEM_ERR_ARG, "mg_setup: smoothing weights must be positive");
+    c->mg_omega2 = omega2;
     return mg_setup(c, dim, coords, bc_mask, lo_host, hi_host, m1_host, nu, omega, max_coarse);
 }
 int sfem_mg_num_levels(sfem_ctx* c) { return c ? mg_num_levels(c) : 0; }

@@ -53,6 +53,7 @@ struct sfem_ctx {
     std::vector<MGLevel*> mg;
     int mg_nu_pre = 2, mg_nu_post = 2;
     double mg_omega = 0.8;
+    double mg_omega2 = 0.8;          // weight of every second sweep (== mg_omega: plain damped Jacobi)
     int tile_rows = 0;               // rows per fine-level chunk of the staged-tile operators (0: default)
     int tile_sw = 0;                 // slab width override for the tile kernels (0: automatic, 32: force 32 columns)
 

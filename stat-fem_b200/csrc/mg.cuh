@@ -22,7 +22,8 @@ struct MGLevel {
     // ---- staged-tile form (mg_tiles.cu): everything below lives in this level's renumbered ("tile") ordering
     int* perm = nullptr;          // [n] tile position -> original index   (nullptr: identity)
     int* iperm = nullptr;         // [n] original index -> tile position
-    double* dinv_t = nullptr;     // [n] smoother scaling in tile ordering
+    double* dinv_t = nullptr;     // [n] smoother scaling in tile ordering (first weight)
+    double* dinv_t2 = nullptr;    // [n] second smoothing weight
     TileOp tA;                    // level operator
     TileOp tP;                    // prolongation from level l+1   (n_l x n_{l+1})
     TileOp tR;                    // restriction to level l+1      (n_{l+1} x n_l)

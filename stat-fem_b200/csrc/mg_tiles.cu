@@ -110,6 +110,14 @@ __global__ void permute_vector_kernel(int64_t n, const int* __restrict__ perm, c
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < n) out[q] = in[perm ? perm[q] : q];
 }
+// second smoothing weight: ratio * dinv on free rows, dinv itself on constrained (identity) rows
+__global__ void second_weight_kernel(int64_t n, const int* __restrict__ perm, const double* __restrict__ dinv,
+                                     const unsigned char* __restrict__ constrained, double ratio, double* __restrict__ out) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int64_t i = perm ? perm[q] : q;
+    out[q] = constrained[i] ? dinv[i] : ratio * dinv[i];
+}
 
 // ------------------------------------------------------------------------------------------------ row generators
 // Each generator enumerates the entries of one row (in the renumbered spaces) through a callback f(col, value).
@@ -307,6 +315,8 @@ void mg_tiles_free(MGLevel* L) {
     if (L->perm) cudaFree(L->perm);
     if (L->iperm) cudaFree(L->iperm);
     if (L->dinv_t) cudaFree(L->dinv_t);
+    if (L->dinv_t2) cudaFree(L->dinv_t2);
+    L->dinv_t2 = nullptr;
     L->perm = L->iperm = nullptr;
     L->dinv_t = nullptr;
     tileop_free(&L->tA);
@@ -392,6 +402,10 @@ int mg_build_tiles(sfem_ctx* c) {
         TRY_CUDA(cudaMalloc(&L->dinv_t, sizeof(double) * (size_t)L->n));
         permute_vector_kernel<<<(unsigned)cdiv64(L->n, 256), 256, 0, c->stream>>>(L->n, L->perm, L->dinv, L->dinv_t);
         c->launches++;
+        TRY_CUDA(cudaMalloc(&L->dinv_t2, sizeof(double) * (size_t)L->n));
+        second_weight_kernel<<<(unsigned)cdiv64(L->n, 256), 256, 0, c->stream>>>(L->n, L->perm, L->dinv, L->constrained,
+                                                                               c->mg_omega2 / c->mg_omega, L->dinv_t2);
+        c->launches++;
     }
     // ---- operators
     {
@@ -466,7 +480,7 @@ int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, d
         double* oth = bufB;
         int done;
         if (nu >= 2) {
-            TileArgs a; a.k = k; a.X = b; a.ldx = k; a.Y = cur; a.ldy = k; a.dinv = L->dinv_t;
+            TileArgs a; a.k = k; a.X = b; a.ldx = k; a.Y = cur; a.ldy = k; a.dinv = L->dinv_t; a.dinv2 = L->dinv_t2;
             int r = tileop_apply(c, tagJ, L->tA, TM_PRESMOOTH2, a, op_bytes(L->tA, 2.0 * L->n, k));
             if (r) return r;
             done = 2;
@@ -478,7 +492,7 @@ int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, d
             done = 1;
         }
         for (; done < nu; ++done) {
-            TileArgs a; a.k = k; a.X = cur; a.ldx = k; a.Y = oth; a.ldy = k; a.B = b; a.ldb = k; a.dinv = L->dinv_t;
+            TileArgs a; a.k = k; a.X = cur; a.ldx = k; a.Y = oth; a.ldy = k; a.B = b; a.ldb = k; a.dinv = (done & 1) ? L->dinv_t2 : L->dinv_t;
             int r = tileop_apply(c, tagJ, L->tA, TM_JACOBI, a, op_bytes(L->tA, 3.0 * L->n, k));
             if (r) return r;
             std::swap(cur, oth);
@@ -545,7 +559,8 @@ int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, d
         rc = tileop_apply(c, TAG_MG_LATTICE, L->tP, TM_MULT_ADD, p, op_bytes(L->tP, 2.0 * L->n + c->mg[l + 1]->n, k));
         if (rc) return rc;
         for (int s = 0; s < nu; ++s) {
-            TileArgs a; a.k = k; a.X = cur; a.ldx = k; a.Y = oth; a.ldy = k; a.B = rhs[l]; a.ldb = k; a.dinv = L->dinv_t;
+            TileArgs a; a.k = k; a.X = cur; a.ldx = k; a.Y = oth; a.ldy = k; a.B = rhs[l]; a.ldb = k;
+            a.dinv = ((nu - 1 - s) & 1) ? L->dinv_t2 : L->dinv_t;      // adjoint of the pre-smoother: weights in reverse order
             rc = tileop_apply(c, TAG_MG_LATTICE, L->tA, TM_JACOBI, a, op_bytes(L->tA, 3.0 * L->n, k));
             if (rc) return rc;
             std::swap(cur, oth);
@@ -560,7 +575,8 @@ int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, d
         for (int s = 0; s < nu; ++s) {
             bool last = (s == nu - 1);
             double* dst = last ? Z : oth0;
-            TileArgs a; a.k = k; a.X = cur0; a.ldx = k; a.Y = dst; a.ldy = k; a.B = R; a.ldb = k; a.dinv = L->dinv_t;
+            TileArgs a; a.k = k; a.X = cur0; a.ldx = k; a.Y = dst; a.ldy = k; a.B = R; a.ldb = k;
+            a.dinv = ((nu - 1 - s) & 1) ? L->dinv_t2 : L->dinv_t;
             a.partials = dot_partials;
             rc = tileop_apply(c, TAG_CSR_JACOBI, L->tA, (last && dot_partials) ? TM_JACOBI_DOT : TM_JACOBI, a, op_bytes(L->tA, 3.0 * L->n, k),
                               last ? nparts : nullptr);

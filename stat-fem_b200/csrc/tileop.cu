@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
         if (HAS_D) {
             double* drow = reinterpret_cast<double*>(st0 + (size_t)(t & 1) * op.st_bytes + op.off_drow);
             for (int r = tid; r < nr; r += blockDim.x) cp8(drow + r, a.dinv + r0 + r);
+            if (MODE == TM_PRESMOOTH2)
+                for (int r = tid; r < nr; r += blockDim.x) cp8(drow + op.R + r, a.dinv2 + r0 + r);
         }
     };
 
@@ -331,9 +333,9 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
             else if (MODE == TM_MULT_DOT) { y0 = acc0; y1 = acc1; d0 = fma(s0, acc0, d0); d1 = fma(s1, acc1, d1); }
             else if (MODE == TM_RESID) { y0 = b0 - acc0; y1 = b1 - acc1; }
             else if (MODE == TM_PRESMOOTH2) {
-                // s = b_i, acc = sum_j (a_ij d_j) b_j:  y = d_i b_i + d_i (b_i - acc)
-                const double di = drow[r];
-                y0 = di * (2.0 * s0 - acc0); y1 = di * (2.0 * s1 - acc1);
+                // s = b_i, acc = sum_j (a_ij d_j) b_j:  y = d_i b_i + d2_i (b_i - acc)
+                const double di = drow[r], di2 = drow[op.R + r];
+                y0 = fma(di2, s0 - acc0, di * s0); y1 = fma(di2, s1 - acc1, di * s1);
             } else {   // Jacobi
                 const double di = drow[r];
                 y0 = fma(di, b0 - acc0, s0); y1 = fma(di, b1 - acc1, s1);
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(256) tileop_direct_kernel(TileDev op, TileArgs
                 else if (MODE == TM_MULT_ADD) y = b0 + acc;
                 else if (MODE == TM_MULT_DOT) { y = acc; d0 = fma(s0, acc, d0); }
                 else if (MODE == TM_RESID) y = b0 - acc;
-                else if (MODE == TM_PRESMOOTH2) y = di * (2.0 * s0 - acc);
+                else if (MODE == TM_PRESMOOTH2) y = fma(a.dinv2[row], s0 - acc, di * s0);
                 else { y = fma(di, b0 - acc, s0); if (MODE == TM_JACOBI_DOT) d0 = fma(b0, y, d0); }
                 if (ok) a.Y[row * a.ldy + col] = y;
             }
@@ -428,7 +430,7 @@ size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d) {
     size_t o_bs = st;
     if (has_b) st += al16((size_t)op.max_rows * SW * sizeof(double));
     size_t o_dr = st;
-    if (has_d) st += al16((size_t)op.max_rows * sizeof(double));
+    if (has_d) st += al16((size_t)op.max_rows * sizeof(double) * (mode == TM_PRESMOOTH2 ? 2 : 1));
     size_t tot = 4 * cb + 2 * st;
     size_t o_red = tot;
     if (has_dot) tot += 16 * 64 * sizeof(double);
@@ -552,9 +554,11 @@ int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv) {
     return SFEM_OK;
 }
 
-int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArgs& a, double bytes, int* nparts) {
+int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArgs& a_in, double bytes, int* nparts) {
     if (nparts) *nparts = 0;
-    if (op.nrows <= 0 || a.k <= 0) return SFEM_OK;
+    if (op.nrows <= 0 || a_in.k <= 0) return SFEM_OK;
+    TileArgs a = a_in;
+    if (!a.dinv2) a.dinv2 = a.dinv;
     TileDev d;
     d.desc = op.desc; d.need = op.need; d.ecol = op.ecol;
     d.eval = (mode == TM_PRESMOOTH2) ? op.eval_scaled : op.eval;

@@ -40,7 +40,7 @@ enum {
     TM_JACOBI = 3,      // Y_i = x_i + d_i (b_i - sum a_ij x_j)
     TM_JACOBI_DOT = 4,  // as TM_JACOBI, dot += b_i Y_i
     TM_RESID = 5,       // Y_i = b_i - sum a_ij x_j
-    TM_PRESMOOTH2 = 6,  // Y_i = d_i (2 x_i - sum a_ij d_j x_j): two damped-Jacobi sweeps from a zero guess, x = rhs
+    TM_PRESMOOTH2 = 6,  // Y_i = d_i x_i + d2_i (x_i - sum a_ij d_j x_j): two weighted-Jacobi sweeps from a zero guess, x = rhs
 };
 
 struct TileArgs {
@@ -49,6 +49,7 @@ struct TileArgs {
     double* Y = nullptr; int64_t ldy = 0;           // output block
     const double* B = nullptr; int64_t ldb = 0;     // right-hand side (Jacobi / residual modes)
     const double* dinv = nullptr;                   // per-row scaling (damping folded in)
+    const double* dinv2 = nullptr;                  // TM_PRESMOOTH2: scaling of the second sweep (nullptr: same as dinv)
     double* partials = nullptr;                     // [TILE_MAX_PARTS][k] per-CTA dot partials (rows actually written: *nparts)
 };
 

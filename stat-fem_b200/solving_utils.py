@@ -13,7 +13,7 @@ from .parallel import EnsembleComm, COMM_SELF, ownership_range
 from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
 
-_KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_size", "mg_nu", "mg_omega",
+_KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_size", "mg_nu", "mg_omega", "mg_omega2",
                       "mg_max_coarse", "workspace_gb"}
 
 
@@ -69,7 +69,10 @@ class SparseSolver(object):
         self.block_size = params.get("block_size", None)
         self.workspace_gb = float(params.get("workspace_gb", 24.))
         self.mg_nu = int(params.get("mg_nu", 2))
+        # damped Jacobi by default (measured on the Poisson meshes of BASELINE.json: as few CG iterations as degree-2
+        # Chebyshev weights); mg_omega2 sets a different weight for every second sweep (polynomial smoothing)
         self.mg_omega = float(params.get("mg_omega", 0.8))
+        self.mg_omega2 = float(params.get("mg_omega2", self.mg_omega))
         self.mg_max_coarse = int(params.get("mg_max_coarse", 600))
         self.n = A.shape[0]
         self.ctx = _lib.new_context()
@@ -99,7 +102,7 @@ class SparseSolver(object):
         while True:
             m3 = (C.c_int * 3)(*(m1 + [1] * (3 - d)))
             rc = lib.sfem_mg_setup(ctx.handle, d, _lib.ptr(self._d_coords), _lib.ptr(self._d_mask), lo3, hi3, m3,
-                                   self.mg_nu, self.mg_omega, self.mg_max_coarse)
+                                   self.mg_nu, self.mg_omega, self.mg_omega2, self.mg_max_coarse)
             if rc == _lib.SFEM_ERR_LIMIT and max(m1) > 3:
                 m1 = [max((m - 1) // 2 + 1, 3) for m in m1]     # mesh edges longer than a lattice cell: coarser lattice
                 continue
