@@ -73,9 +73,16 @@ class EnsembleComm(object):
         if self._dist is None or self.size == 1:
             return [local]
         import torch
-        outs = [torch.empty((local.shape[0], int(cnt)), dtype=local.dtype, device=local.device) for cnt in counts]
-        self._dist.all_gather(outs, local.contiguous(), group=self.group)
-        return outs
+        cmax = int(max(counts))
+        m = int(local.shape[0])
+        if int(local.shape[1]) == cmax:
+            send = local.contiguous()
+        else:       # collectives need equal shapes: pad the narrower blocks (PETSc ownership differs by at most one)
+            send = torch.zeros((m, cmax), dtype=local.dtype, device=local.device)
+            send[:, :local.shape[1]] = local
+        outs = [torch.empty((m, cmax), dtype=local.dtype, device=local.device) for _ in counts]
+        self._dist.all_gather(outs, send, group=self.group)
+        return [o[:, :int(cnt)] for o, cnt in zip(outs, counts)]
 
     def gather_rows_to_root(self, local, counts, root=0):
         """local: tensor (counts[rank] x m) of result rows; returns the (sum(counts) x m) concatenation on root, None
@@ -98,7 +105,13 @@ class EnsembleComm(object):
             else:
                 self._dist.send(local.contiguous(), dst=root, group=self.group)
         else:
-            self._dist.gather(local.contiguous(), outs, dst=root, group=self.group)
+            rmax = int(max(counts))
+            send = torch.zeros((rmax, local.shape[1]), dtype=local.dtype, device=local.device)
+            send[:local.shape[0]] = local
+            bufs = [torch.empty_like(send) for _ in counts] if self.rank == root else None
+            self._dist.gather(send, bufs, dst=root, group=self.group)
+            if self.rank == root:
+                outs = [b[:int(cnt)] for b, cnt in zip(bufs, counts)]
         return torch.cat(outs, dim=0) if self.rank == root else None
 
 

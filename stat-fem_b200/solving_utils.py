@@ -208,6 +208,32 @@ def solve_forcing_covariance(G, ls, rhs):
     return f.vector()
 
 
+def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_bytes=2.e9):
+    """The exchange step of the sharded covariance assembly.  Rank r holds ``Wr`` (n x its columns of the right
+    matrix) and ``Zl`` (n x its columns of the left matrix).  Row chunks of ``Zl`` are all-gathered and every rank
+    accumulates its rows ``Wr^T Z_left`` of the (n_right x n_left) result with ``gemm_tn(W_chunk, Z_chunk, out, beta)``
+    (out = W_chunk^T Z_chunk + beta out); the row blocks are then gathered on rank 0 in ownership order -- the
+    ``Scatter.toZero`` of solving_utils.py:146-159.  Returns the full array on rank 0, None elsewhere."""
+    size = ensemble_comm.size
+    n = int(Wr.shape[0])
+    nloc = int(Wr.shape[1])
+    res = zeros((max(nloc, 1), n_left))[:nloc]
+    if size == 1:
+        if nloc and n_left:
+            gemm_tn(Wr, Zl, res, 0.0)
+        return res
+    lcounts = [ownership_range(n_left, s, size) for s in range(size)]
+    chunk = max(1024, min(n, int(chunk_bytes / (8. * max(n_left, 1)))))
+    for k0 in range(0, n, chunk):
+        k1 = min(n, k0 + chunk)
+        pieces = ensemble_comm.all_gather_rows(Zl[k0:k1, :], [b - a for a, b in lcounts])
+        for (a, b), piece in zip(lcounts, pieces):
+            if nloc and b > a:
+                gemm_tn(Wr[k0:k1], piece, res[:, a:b], 1.0)
+    rcounts = [ownership_range(n_right, s, size) for s in range(size)]
+    return ensemble_comm.gather_rows_to_root(res.contiguous(), [b - a for a, b in rcounts])
+
+
 def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF, return_device=False):
     """Phi_l^T A^-1 G A^-1 Phi_r on the root process, ``(0, 0)`` elsewhere (solving_utils.py:61-169).
 
@@ -252,29 +278,12 @@ def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF,
         Zl = ctx.empty((n, max(lmax - lmin, 1)))[:, :lmax - lmin]
         if lmax > lmin:
             ls.solve_columns(im_left.csc, lmin, lmax - lmin, Zl)
-    # rows [imin, imax) of the (n_right x n_left) array  W^T Z_left
-    res = ctx.zeros((max(nloc, 1), n_left))[:nloc]
-    if size == 1:
-        if nloc and n_left:
-            ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, nloc, n_left, n, 1.0, _lib.ptr(Wr), int(Wr.stride(0)),
-                                     _lib.ptr(Zl), int(Zl.stride(0)), 0.0, _lib.ptr(res), int(res.stride(0))))
-    else:
-        lcounts = [ownership_range(n_left, s, size) for s in range(size)]
-        chunk = max(1024, min(n, int(2.e9 / (8. * max(n_left, 1)))))
-        for k0 in range(0, n, chunk):
-            k1 = min(n, k0 + chunk)
-            pieces = ensemble_comm.all_gather_rows(Zl[k0:k1, :], [b - a for a, b in lcounts])
-            for (a, b), piece in zip(lcounts, pieces):
-                if nloc and b > a:
-                    sub = res[:, a:b]
-                    ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, nloc, b - a, k1 - k0, 1.0,
-                                             _lib.ptr(Wr[k0:k1]), int(Wr.stride(0)), _lib.ptr(piece), int(piece.stride(0)),
-                                             1.0, _lib.ptr(sub), int(sub.stride(0))))
-    if size > 1:
-        rcounts = [ownership_range(n_right, s, size) for s in range(size)]
-        full = ensemble_comm.gather_rows_to_root(res.contiguous(), [b - a for a, b in rcounts])
-    else:
-        full = res
+    # rows [imin, imax) of the (n_right x n_left) array  W^T Z_left, gathered on the ensemble root
+    def gemm_tn(Wb, Zb, out, beta):
+        ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, int(Wb.shape[1]), int(Zb.shape[1]), int(Wb.shape[0]), 1.0,
+                                 _lib.ptr(Wb), int(Wb.stride(0)), _lib.ptr(Zb), int(Zb.stride(0)), beta,
+                                 _lib.ptr(out), int(out.stride(0))))
+    full = sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, ctx.zeros)
     if im_left.comm.rank == 0 and rank == 0:
         out = full.reshape(-1).reshape(n_left, n_right)      # the reference's reshape (lines 164-169)
         return out if return_device else out.cpu().numpy()

@@ -1,0 +1,89 @@
+"""World-size-2 CPU test (gloo) of the host-side sharding logic: PETSc-style column ownership, the all-gather /
+accumulate / gather-to-root exchange of the sharded covariance assembly (solving_utils.sharded_wtz, the step that
+replaces solving_utils.py:117-159 of the reference), object broadcast and allreduce.  The GEMM is a torch.mm stand-in
+here; on the GPU the same function is driven with the DMMA GEMM of the library."""
+import os
+import socket
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, n_left, n_right, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import stat_fem_b200  # noqa: F401  (import shim; no GPU is touched by the functions used here)
+        from stat_fem_b200.parallel import EnsembleComm, ownership_range
+        from stat_fem_b200.solving_utils import sharded_wtz
+        comm = EnsembleComm()
+        assert (comm.rank, comm.size) == (rank, world)
+        rng = np.random.default_rng(7)
+        Z_left = torch.from_numpy(rng.normal(size=(n, n_left)))
+        W_right = torch.from_numpy(rng.normal(size=(n, n_right)))
+        imin, imax = comm.column_range(n_right)
+        lmin, lmax = comm.column_range(n_left)
+        assert (imin, imax) == ownership_range(n_right, rank, world)
+
+        def gemm_tn(Wb, Zb, out, beta):
+            out.copy_(Wb.t() @ Zb + beta * out)
+
+        full = sharded_wtz(comm, W_right[:, imin:imax].contiguous(), Z_left[:, lmin:lmax].contiguous(), n_left, n_right,
+                           gemm_tn, lambda shape: torch.zeros(shape, dtype=torch.float64), chunk_bytes=8. * n_left * 1500)
+        got = comm.bcast({"k": rank} if rank == 0 else None, root=0)
+        assert got == {"k": 0}
+        tot = comm.allreduce(np.array([float(rank + 1)]))
+        assert tot[0] == sum(range(1, world + 1))
+        comm.barrier()
+        if rank == 0:
+            ref = (W_right.t() @ Z_left).numpy()
+            err = float(np.max(np.abs(full.numpy() - ref)) / np.max(np.abs(ref)))
+            out_q.put(("ok", err, tuple(full.shape)))
+        else:
+            assert full is None
+            out_q.put(("ok", 0.0, None))
+    except Exception as exc:     # pragma: no cover - reported to the parent
+        out_q.put(("fail", repr(exc), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,n_left,n_right", [(4000, 7, 7), (3001, 5, 9), (2500, 1, 3)])
+def test_sharded_wtz_world2(n, n_left, n_right):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, n_left, n_right, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for status, val, shape in results:
+        assert status == "ok", val
+        assert val < 1e-13
+    shapes = [s for _, _, s in results if s is not None]
+    assert shapes == [(n_right, n_left)]
+
+
+def test_ownership_ranges_match_petsc_rule():
+    from stat_fem_b200.parallel import ownership_range
+    for n in (0, 1, 7, 100, 4096):
+        for size in (1, 2, 3, 8):
+            ranges = [ownership_range(n, r, size) for r in range(size)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(size - 1))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
