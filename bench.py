@@ -3,7 +3,8 @@
 
 One *step* = one full pass of the hot path over one synthetic problem (BASELINE.json config 2 by default):
     G assembly -> stiffness upload + multigrid setup -> Z = A^-1 P (n_obs columns) -> W = G Z -> Cu = W^T Z, mu
-    -> for each of the data snapshots: MAP estimate (L-BFGS-B, start 0) + posterior mean on the mesh.
+    -> for each of the data snapshots: MAP estimate (L-BFGS-B, start 0) + posterior mean on the mesh (the snapshots'
+       fits run concurrently on separate streams; their mean solves advance together as block solves).
 `value`  : seconds per step with every input already resident in HBM and no result copied back (device-timed).
 `e2e`    : seconds per step through the public drop-in API with HOST buffers (NumPy in, NumPy out).
 `roofline`: the stiffness-operator kernel family (tileop_kernel on the fine level: q = A p, Jacobi sweeps, residual),
@@ -63,7 +64,7 @@ def gpu_step(prob, comm, resident, stats=None):
     """one pass of the hot path through the drop-in API; returns a small dict of results"""
     import stat_fem_b200 as stat_fem
     from stat_fem_b200 import fem
-    from stat_fem_b200.estimation import fit_linear_solver
+    from stat_fem_b200.estimation import fit_snapshots
     V, A, b = prob["V"], prob["A"], prob["b"]
     G = stat_fem.ForcingCovariance(V, prob["sigma_f"], prob["l_f"], prob["cutoff"], prob["reg"])
     G.assemble()
@@ -75,19 +76,24 @@ def gpu_step(prob, comm, resident, stats=None):
     ls.host_results = not resident
     mu, Cu = ls.solve_prior()
     out = dict(nnzG=G.G.nnz, iters=list(ls.solver.block_iterations), thetas=[], evals=0)
-    xs = []
-    for s, od in enumerate(ods):
-        lss = ls if s == 0 else ls.clone_for_data(od)
-        fit_linear_solver(lss, start=np.zeros(3))
+    # the snapshots share the sensors, hence the prior: their MAP fits run concurrently (one stream each) and their
+    # posterior means are advanced together as block solves
+    solvers = fit_snapshots(ls, ods, start=np.zeros(3))
+    for lss in solvers:
         out["thetas"].append(lss.params.copy())
         out["evals"] += lss.n_logpost_evals
-        x = fem.Function(V)
-        lss.solve_posterior(x, scale_mean=True)
-        xs.append(x)
+    xs = [fem.Function(V) for _ in ods]
+    stat_fem.solve_posterior_snapshots(solvers, xs, scale_mean=True)
     out["mu0"] = float(mu[0]) if len(mu) else 0.
     out["x_norm"] = float(np.linalg.norm(xs[-1].data))
     if stats is not None:
-        stats["profile"] = ls.solver.ctx.profile_read()
+        # per-family totals over the sparse-solver context and the snapshots' dense contexts
+        prof = ls.solver.ctx.profile_read()
+        for ctx in {id(s.dctx): s.dctx for s in solvers if s.dctx is not ls.solver.ctx}.values():
+            for tag, v in ctx.profile_read().items():
+                for key in ("ms", "bytes", "flops", "count"):
+                    prof[tag][key] += v[key]
+        stats["profile"] = prof
     out["ls"], out["G"] = ls, G
     return out
 
@@ -282,8 +288,8 @@ class _ProfileHook(object):
         mask = self.mask
         orig = self._orig
 
-        def init(ctx_self, device=None):
-            orig(ctx_self, device)
+        def init(ctx_self, *a, **kw):
+            orig(ctx_self, *a, **kw)
             ctx_self.profile_enable(mask)
         _lib.Context.__init__ = init
         for c in _lib._live:

@@ -58,10 +58,12 @@ class LinearSolver(object):
         self.n_logpost_evals = 0
         self.host_results = True        # False: leave Cu on the device in solve_prior (bench.py's device-resident arm)
 
-    def clone_for_data(self, data):
+    def clone_for_data(self, data, private_stream=False):
         """A LinearSolver for another data set at the SAME sensor locations that shares this one's stiffness solver,
         interpolation matrix and cached prior (x, mu, Cu).  Extension over the reference, whose caches are per object
-        (LinearSolver.py:150-153): several data snapshots on one sensor array need the n_obs solves only once."""
+        (LinearSolver.py:150-153): several data snapshots on one sensor array need the n_obs solves only once.
+        ``private_stream``: give the clone its own CUDA stream + context for the dense n_obs x n_obs work, so that
+        clones driven from different host threads run concurrently on the GPU (estimation.fit_snapshots)."""
         if not isinstance(data, ObsData):
             raise TypeError("data must be an ObsData type")
         assert np.array_equal(data.get_coords(), self.data.get_coords()), "snapshots must share the sensor locations"
@@ -71,14 +73,35 @@ class LinearSolver(object):
         other._owns_im = False
         other.params = None
         other._cache = None
-        other._dense_work = self._dense_work
+        other._dense_work = None if private_stream else self._dense_work
+        other._dense_ctx = _lib.new_stream_context() if private_stream else self.__dict__.get("_dense_ctx")
+        other._owns_dense_ctx = bool(private_stream)
+        other._data_dev = None
         other.n_logpost_evals = 0
         return other
+
+    @property
+    def dctx(self):
+        "context (device + stream) of the dense data-space work"
+        return self.__dict__.get("_dense_ctx") or self.solver.ctx
+
+    def _data_device(self):
+        "device copies of the sensor coordinates / data / uncertainties, ordered on this solver's dense stream"
+        if self.__dict__.get("_dense_ctx") is None:
+            return self.data.device()
+        if self.__dict__.get("_data_dev") is None:
+            ctx, od = self.dctx, self.data
+            self._data_dev = dict(ctx=ctx, coords=ctx.to_device(od.coords, np.float64), data=ctx.to_device(od.data, np.float64),
+                                  unc=ctx.to_device(np.atleast_1d(od.unc), np.float64), unc_vec=int(od.unc.shape != ()))
+        return self._data_dev
 
     def __del__(self):
         try:
             if self.__dict__.get("_owns_im", True):
                 self.im.destroy()
+            if self.__dict__.get("_owns_dense_ctx", False):
+                self._dense_work = None
+                _lib.destroy_context(self._dense_ctx)
         except Exception:
             pass
 
@@ -97,7 +120,7 @@ class LinearSolver(object):
         n = self.data.get_n_obs()
         need = _lib.lib().sfem_dense_workspace_bytes(n)
         if self._dense_work is None or self._dense_work.numel() < need + 256:
-            self._dense_work = self.solver.ctx.workspace(need)
+            self._dense_work = self.dctx.workspace(need)
         w = self._dense_work
         off = (-w.data_ptr()) % 256
         return C.c_void_p(w.data_ptr() + off), int(w.numel() - off)
@@ -126,8 +149,8 @@ class LinearSolver(object):
         return self.mu, self.Cu
 
     def _dense_solve(self, rho2, with_Cu, b_dev):
-        d = self.data.device()
-        ctx = self.solver.ctx
+        d = self._data_device()
+        ctx = self.dctx
         out = ctx.empty((self.data.get_n_obs(),))
         work, nbytes = self._work()
         ctx.check(_lib.lib().sfem_dense_solve(ctx.handle, self.data.get_n_obs(), self.data.get_n_dim(), _lib.ptr(d["coords"]),
@@ -326,8 +349,8 @@ class LinearSolver(object):
         world = comm_world()
         if world.rank == 0:
             n = self.data.get_n_obs()
-            d = self.data.device()
-            ctx = self.solver.ctx
+            d = self._data_device()
+            ctx = self.dctx
             theta = (C.c_double * 3)(*self.params)
             value = C.c_double(0.)
             grad = (C.c_double * 3)()
@@ -358,3 +381,59 @@ class LinearSolver(object):
         "gradient of the negative log posterior wrt the three log-parameters (LinearSolver.py:625-691)"
         _, grad = self._evaluate(params, need_grad=True)
         return grad.copy()
+
+
+def solve_posterior_snapshots(solvers, xs, scale_mean=False):
+    """Posterior means on the mesh for several fitted LinearSolvers that share one prior (``clone_for_data``): the
+    arithmetic of ``solve_posterior`` (LinearSolver.py:259-305) for every snapshot, with the 4 mesh-space solves of
+    each snapshot advanced together as 4 block solves of ``len(solvers)`` columns.  ``xs[s]`` receives the mean of
+    snapshot s.  Extension over the reference API (which handles one data set per LinearSolver)."""
+    import torch
+    if not isinstance(bool(scale_mean), bool):
+        raise TypeError("scale_mean argument must be boolean-like")
+    assert len(solvers) == len(xs) and len(solvers) > 0
+    base = solvers[0]
+    for ls in solvers:
+        if ls.Cu is None or ls.x is None:
+            ls.solve_prior()
+        if ls.params is None:
+            raise ValueError("must set parameter values to solve posterior")
+        assert ls.solver is base.solver and ls.im is base.im, "snapshots must share the prior (clone_for_data)"
+    if base.ensemble_comm.rank != 0:
+        return
+    sp, G, im, ctx = base.solver, base.G, base.im, base.solver.ctx
+    ns, n, nobs = len(solvers), sp.n, base.data.get_n_obs()
+    rhos = [float(np.exp(ls.params[0])) for ls in solvers]
+
+    def dense_cols(rho2s, with_Cu, rhs_cols):
+        out = ctx.empty((nobs, ns))
+        ctx.sync()                       # right-hand sides were produced on the main stream; clones may use their own
+        for s, ls in enumerate(solvers):
+            try:
+                col = ls._dense_solve(rho2s[s], with_Cu, rhs_cols[s])
+            except LinAlgError:
+                raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy" +
+                                  (" plus forcing covariance" if with_Cu else ""))
+            if ls.dctx is not ctx:
+                ls.dctx.sync()
+            out[:, s] = col
+        return out
+
+    def aga(M):      # A^-1 G A^-1 on a block of columns, Dirichlet lifting off (solving_utils.py:46-57)
+        X = ctx.empty((n, ns))
+        sp.solve_block(M, X)
+        Wb = G.G.matmul(X)
+        sp.solve_block(Wb, X)
+        return X
+
+    T1 = dense_cols([0.] * ns, False, [ls._data_device()["data"] for ls in solvers])
+    M2 = aga(im.csr.matmul(T1))                                     # (n x ns)
+    M2 = M2 * torch.tensor(rhos, dtype=torch.float64, device=M2.device)[None, :] + base._x_dev[:, None]
+    D1 = im.csc.matmul(M2.contiguous())                             # (n_obs x ns)
+    D2 = dense_cols([r * r for r in rhos], True, [D1[:, s].contiguous() for s in range(ns)])
+    M3 = aga(im.csr.matmul(D2))
+    for s, (ls, x) in enumerate(zip(solvers, xs)):
+        sf = rhos[s] if scale_mean else 1.
+        out = sf * M2[:, s] - sf * rhos[s] ** 2 * M3[:, s]
+        xf = x.function if isinstance(x, fem.Vector) else x
+        xf.data[:] = out.cpu().numpy()

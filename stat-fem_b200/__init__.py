@@ -10,10 +10,10 @@ from .parallel import EnsembleComm, COMM_SELF, comm_world
 from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix, interpolate_cell
 from .ObsData import ObsData
-from .LinearSolver import LinearSolver
+from .LinearSolver import LinearSolver, solve_posterior_snapshots
 from .solving import solve_posterior, solve_posterior_covariance, solve_prior
 from .solving import solve_prior_generating, solve_posterior_generating
 from .solving import predict_mean, predict_covariance
-from .estimation import estimate_params_MAP
+from .estimation import estimate_params_MAP, fit_snapshots
 from .assemble import assemble
 from . import covariance_functions

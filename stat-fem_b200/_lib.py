@@ -100,14 +100,15 @@ def torch_mod():
 class Context(object):
     """One sfem_ctx per CUDA device, bound to torch's current stream on that device."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, stream=None):
         torch = torch_mod()
         if not torch.cuda.is_available():
             raise RuntimeError("stat-fem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.tdev = torch.device("cuda", self.device)
         self.handle = C.c_void_p()
-        stream = torch.cuda.current_stream(self.tdev).cuda_stream
+        self.tstream = stream            # a torch.cuda.Stream this context is bound to (None: the stream current now)
+        stream = (stream if stream is not None else torch.cuda.current_stream(self.tdev)).cuda_stream
         rc = lib().sfem_create(C.byref(self.handle), self.device, C.c_void_p(stream))
         if rc != 0:
             raise RuntimeError("sfem_create failed (rc=%d): %s" % (rc, lib().sfem_last_error(None).decode()))
@@ -214,6 +215,15 @@ class DeviceCSR(object):
 def new_context(device=None):
     "a private context (own stiffness matrix + multigrid hierarchy), e.g. one per SparseSolver"
     return Context(device)
+
+
+def new_stream_context(device=None):
+    """a private context on its OWN CUDA stream: independent dense work (e.g. the MAP fits of several data snapshots)
+    submitted from different host threads overlaps on the GPU.  Callers make that stream current in their thread
+    (``torch.cuda.stream(ctx.tstream)``) so that torch allocations and copies are ordered with the library's kernels."""
+    torch = torch_mod()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    return Context(dev, stream=torch.cuda.Stream(device=dev))
 
 
 def destroy_context(ctx):

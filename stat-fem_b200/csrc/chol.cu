@@ -252,9 +252,13 @@ static void* dense_tmp(sfem_ctx* c, size_t bytes) {
 }
 
 // dinv: device buffer of ceil(n/128) * 128*128 doubles.  info_dev: device int (zeroed here).
-// Right-looking, 128-wide panels.  The panel solve writes to a temporary (so it may use small tiles and fill the
-// machine), the trailing update reads that temporary, and the copy back into A is off the critical path.
+// Two-level right-looking factorisation: 128-wide panels inside 512-wide column blocks.  Inside a column block the
+// rank-128 updates touch only the block's own columns; the trailing matrix is updated once per column block with
+// K = 512, where the DMMA GEMM runs at full pipeline efficiency (a K = 128 update is mostly pipeline fill and C
+// traffic).  The panel solve writes to a temporary (so it may use small tiles and fill the machine) and the copy back
+// into A is off the critical path.
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
+    constexpr int NB2 = 512;
     CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
     size_t dyn = sizeof(double) * (NB * PLD + 4 * SB * DLD + NB);
     static bool attr_set = false;
@@ -267,28 +271,39 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
         T = (double*)dense_tmp(c, sizeof(double) * (size_t)n * NB);
         if (!T) return sfem_fail(c, SFEM_ERR_CUDA, "potrf: temporary allocation failed");
     }
-    for (int j0 = 0; j0 < n; j0 += NB) {
-        int nb = imin(NB, n - j0);
-        double* Ajj = A + (int64_t)j0 * lda + j0;
-        double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
-        {
-            ProfScope ps(c, TAG_POTRF_PANEL, 24.0 * nb * nb, (2.0 / 3.0) * nb * nb * nb);
-            potrf_panel_kernel<<<1, 256, dyn, c->stream>>>(Ajj, lda, nb, j0, Dj, info_dev);
-            KCHECK(c);
-        }
-        int m = n - j0 - nb;
-        if (m > 0) {
+    for (int J0 = 0; J0 < n; J0 += NB2) {
+        const int Jend = imin(J0 + NB2, n);           // one past the last column of this column block
+        for (int j0 = J0; j0 < Jend; j0 += NB) {
+            int nb = imin(NB, n - j0);
+            double* Ajj = A + (int64_t)j0 * lda + j0;
+            double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
+            {
+                ProfScope ps(c, TAG_POTRF_PANEL, 24.0 * nb * nb, (2.0 / 3.0) * nb * nb * nb);
+                potrf_panel_kernel<<<1, 256, dyn, c->stream>>>(Ajj, lda, nb, j0, Dj, info_dev);
+                KCHECK(c);
+            }
+            int m = n - j0 - nb;
+            if (m <= 0) continue;
             double* A21 = A + (int64_t)(j0 + nb) * lda + j0;
             double* A22 = A + (int64_t)(j0 + nb) * lda + (j0 + nb);
             c->dgemm_tag = TAG_CHOL_TRSM;
             int rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);   // T = A21 inv(L_jj)^T
             c->dgemm_tag = TAG_CHOL_SYRK;
-            if (rc) return rc;
-            rc = dgemm(c, OP_N, OP_T, m, m, nb, -1.0, T, NB, T, NB, 1.0, A22, lda, 1);             // SYRK, lower tiles
+            int ncols = Jend - (j0 + nb);              // columns of this column block still to be updated
+            if (rc == SFEM_OK && ncols > 0)
+                rc = dgemm(c, OP_N, OP_T, m, ncols, nb, -1.0, T, NB, T, NB, 1.0, A22, lda, 1);   // lower tiles
             c->dgemm_tag = TAG_DGEMM;
             if (rc) return rc;
             CUDA_TRY(c, cudaMemcpy2DAsync(A21, sizeof(double) * lda, T, sizeof(double) * NB, sizeof(double) * nb, m,
                                           cudaMemcpyDeviceToDevice, c->stream));
+        }
+        int m2 = n - Jend;
+        if (m2 > 0) {
+            const double* L2 = A + (int64_t)Jend * lda + J0;     // finished rows below the column block, its columns
+            c->dgemm_tag = TAG_CHOL_SYRK;
+            int rc = dgemm(c, OP_N, OP_T, m2, m2, Jend - J0, -1.0, L2, lda, L2, lda, 1.0, A + (int64_t)Jend * lda + Jend, lda, 1);
+            c->dgemm_tag = TAG_DGEMM;
+            if (rc) return rc;
         }
     }
     return SFEM_OK;

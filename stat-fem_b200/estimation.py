@@ -43,3 +43,44 @@ def fit_linear_solver(ls, start=None, **minimize_kwargs):
     ls.set_params(root_result)
     ls.minimize_result = fmin_dict
     return ls
+
+
+def fit_snapshots(ls, datas, start=None, concurrent=True, **minimize_kwargs):
+    """MAP fits for several data snapshots taken at the SAME sensors: the prior (x, mu, Cu) of ``ls`` is shared
+    (``LinearSolver.clone_for_data``) and, on a single process, every snapshot's L-BFGS-B loop runs in its own host
+    thread on its own CUDA stream, so that the latency-bound parts of one fit (Cholesky panels, small GEMMs) overlap
+    with the throughput-bound parts of the others.  Returns the list of fitted LinearSolvers (``ls`` itself is used
+    for ``datas[0]`` when that is its own data set).  Extension over the reference API."""
+    import threading
+    import torch
+    if ls.Cu is None or ls.mu is None:
+        ls.solve_prior()
+    world = comm_world()
+    conc = bool(concurrent) and world.size == 1 and len(datas) > 1
+    solvers = []
+    for od in datas:
+        solvers.append(ls if (od is ls.data and not conc) else ls.clone_for_data(od, private_stream=conc))
+    if not conc:
+        for s in solvers:
+            fit_linear_solver(s, start=start, **minimize_kwargs)
+        return solvers
+    torch.cuda.synchronize()                  # the shared prior is complete before the side streams read it
+    errors = [None] * len(solvers)
+
+    def work(i):
+        try:
+            with torch.cuda.stream(solvers[i].dctx.tstream):
+                fit_linear_solver(solvers[i], start=start, **minimize_kwargs)
+                solvers[i].dctx.sync()
+        except BaseException as exc:      # re-raised in the caller
+            errors[i] = exc
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(solvers))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for exc in errors:
+        if exc is not None:
+            raise exc
+    return solvers

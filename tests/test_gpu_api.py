@@ -210,3 +210,48 @@ def test_cu_full_size_property():
     omu = P.T @ ols.solver.solve(b.data, bcs_on=True)
     assert relerr(mu, omu) < TOL
     print("257^2: CG iterations per block", ls.solver.block_iterations, "levels", ls.solver.mg_levels)
+
+
+def test_snapshots_concurrent_fit_and_block_posterior_means():
+    """Extension API for several data snapshots on one sensor array: fit_snapshots (one stream + host thread per
+    snapshot) and solve_posterior_snapshots (block solves) must reproduce the one-at-a-time reference-style calls."""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    from stat_fem_b200.estimation import fit_linear_solver
+    nodes = 65
+    V, A, b = fem.poisson_problem(nodes, 2)
+    h = 1. / (nodes - 1)
+    sig, l = np.log(2.e-2), np.log(1.5 * h)
+    reg = 1.e-8 * h ** 4 * np.exp(2 * sig)
+    rng = np.random.default_rng(3)
+    s = rng.uniform(0.05, 0.95, (40, 2))
+    truth = 0.7 * np.sin(2 * np.pi * s[:, 0]) * np.sin(2 * np.pi * s[:, 1])
+    datas = [stat_fem.ObsData(s, truth + rng.normal(scale=5e-3, size=40), 2.e-3) for _ in range(3)]
+    G = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg)
+    ls = stat_fem.LinearSolver(A, b, G, datas[0])
+    ls.solve_prior()
+    # one at a time (the reference's way)
+    seq, xs_seq = [], []
+    for od in datas:
+        one = ls.clone_for_data(od)
+        fit_linear_solver(one, start=np.zeros(3))
+        x = fem.Function(V)
+        one.solve_posterior(x, scale_mean=True)
+        seq.append(one)
+        xs_seq.append(x.data.copy())
+    # concurrent fits + block posterior means
+    con = stat_fem.fit_snapshots(ls, datas, start=np.zeros(3))
+    xs = [fem.Function(V) for _ in datas]
+    stat_fem.solve_posterior_snapshots(con, xs, scale_mean=True)
+    for a, c, x, xr in zip(seq, con, xs, xs_seq):
+        assert_allclose(c.params, a.params, rtol=1e-6, atol=1e-6)
+        assert abs(c.logposterior(c.params) - a.logposterior(a.params)) <= TOL_LP * max(1., abs(a.logposterior(a.params)))
+        assert relerr(x.data, xr) < 1e-6      # same optimum to 1e-6 -> same mean to that order
+    # same parameters on both sides: the block path itself agrees to solver accuracy
+    for a, c in zip(seq, con):
+        c.set_params(a.params)
+    stat_fem.solve_posterior_snapshots(con, xs, scale_mean=False)
+    for a, x in zip(seq, xs):
+        xr = fem.Function(V)
+        a.solve_posterior(xr, scale_mean=False)
+        assert relerr(x.data, xr.data) < TOL
