@@ -85,6 +85,7 @@ def gpu_step(prob, comm, resident, stats=None):
     xs = [fem.Function(V) for _ in ods]
     stat_fem.solve_posterior_snapshots(solvers, xs, scale_mean=True)
     out["mu0"] = float(mu[0]) if len(mu) else 0.
+    out["cu_checksum"] = float(Cu.sum()) if comm.rank == 0 else 0.       # same value at every N: the sharded path is exact
     out["x_norm"] = float(np.linalg.norm(xs[-1].data))
     if stats is not None:
         # per-family totals over the sparse-solver context and the snapshots' dense contexts
@@ -257,7 +258,8 @@ def run_gpu(args):
                    "parallelism": "observation columns sharded over %d GPU(s)" % world,
                    "l2": "working set (>= %.1f GB per vector block) exceeds the 126 MB L2; no flush needed" %
                          (8e-9 * prob["V"].dim() * min(prob["nobs"], 384)),
-                   "cg_iterations_per_block": res["iters"], "map_evaluations": res["evals"]},
+                   "cg_iterations_per_block": res["iters"], "map_evaluations": res["evals"],
+                   "cu_checksum": res["cu_checksum"], "theta_snapshot0": [float(t) for t in res["thetas"][0]]},
         "e2e": {"value": e2e_wall / e2e_steps, "unit": "s", "h2d_bytes_per_step": bytes_h2d(prob),
                 "d2h_bytes_per_step": bytes_d2h(prob), "steps": e2e_steps},
         "gpu_launches": int(launches),

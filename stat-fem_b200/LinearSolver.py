@@ -339,7 +339,10 @@ class LinearSolver(object):
 
     # ---------------------------------------------------------------------------------------------------------
     def _evaluate(self, params, need_grad):
-        "negative log marginal likelihood (and gradient) on the device; identical result on every process"
+        """negative log marginal likelihood (and gradient) on the device; identical result on every process.  In the
+        reference every process runs the optimiser in lock-step and the value is broadcast from rank 0 at each
+        evaluation (LinearSolver.py:615-621).  After ``share_prior`` every process holds mu and Cu, evaluates locally
+        and no per-evaluation collective is needed (``self._local_eval``, used by estimation.fit_snapshots)."""
         self.set_params(params)
         if self.Cu is None or self.mu is None:
             self.solve_prior()
@@ -347,7 +350,8 @@ class LinearSolver(object):
         if self._cache is not None and self._cache[0] == key and (self._cache[2] is not None or not need_grad):
             return self._cache[1], self._cache[2]
         world = comm_world()
-        if world.rank == 0:
+        local = bool(self.__dict__.get("_local_eval", False)) and self._Cu_dev is not None
+        if world.rank == 0 or local:
             n = self.data.get_n_obs()
             d = self._data_device()
             ctx = self.dctx
@@ -366,11 +370,34 @@ class LinearSolver(object):
             result = (float(value.value), np.array(list(grad), dtype=np.float64) if need_grad else None)
         else:
             result = None
-        result = world.bcast(result, root=0)
-        assert result is not None, "error in broadcasting the log likelihood"
-        world.barrier()
+        if not local:
+            result = world.bcast(result, root=0)
+            assert result is not None, "error in broadcasting the log likelihood"
+            world.barrier()
         self._cache = (key, result[0], result[1])
         return result
+
+    def share_prior(self):
+        """Broadcast the cached prior (x, mu, Cu) from ensemble rank 0 to every rank's GPU (NCCL over NVLink; 134 MB
+        at 4096 sensors), so that every rank can run the dense data-space work -- e.g. the MAP fits of different data
+        snapshots -- on its own.  No counterpart in the reference, whose dense end runs on rank 0 only."""
+        comm = self.ensemble_comm
+        if comm.size == 1 or self.__dict__.get("_prior_shared", False):
+            return
+        if self.Cu is None or self.mu is None:
+            self.solve_prior()
+        ctx = self.solver.ctx
+        n_obs, n = self.data.get_n_obs(), self.solver.n
+        if comm.rank != 0:
+            self._Cu_dev = ctx.empty((n_obs, n_obs))
+            self._mu_dev = ctx.empty((n_obs,))
+            self._x_dev = ctx.empty((n,))
+        for t in (self._Cu_dev, self._mu_dev, self._x_dev):
+            comm.broadcast_tensor(t, root=0)
+        if comm.rank != 0:
+            self.mu = self._mu_dev.cpu().numpy()
+            self.Cu = self._Cu_dev if not self.host_results else self._Cu_dev.cpu().numpy()
+        self._prior_shared = True
 
     def logposterior(self, params):
         "negative log posterior (LinearSolver.py:569-623); priors are always None (LinearSolver.py:130-132)"
@@ -386,8 +413,10 @@ class LinearSolver(object):
 def solve_posterior_snapshots(solvers, xs, scale_mean=False):
     """Posterior means on the mesh for several fitted LinearSolvers that share one prior (``clone_for_data``): the
     arithmetic of ``solve_posterior`` (LinearSolver.py:259-305) for every snapshot, with the 4 mesh-space solves of
-    each snapshot advanced together as 4 block solves of ``len(solvers)`` columns.  ``xs[s]`` receives the mean of
-    snapshot s.  Extension over the reference API (which handles one data set per LinearSolver)."""
+    each snapshot advanced together as 4 block solves.  On several processes whose prior has been shared
+    (``share_prior``, done by ``fit_snapshots``) the snapshots are dealt out round-robin and the means are collected on
+    rank 0.  ``xs[s]`` receives the mean of snapshot s on the ensemble root.  Extension over the reference API (which
+    handles one data set per LinearSolver)."""
     import torch
     if not isinstance(bool(scale_mean), bool):
         raise TypeError("scale_mean argument must be boolean-like")
@@ -399,41 +428,57 @@ def solve_posterior_snapshots(solvers, xs, scale_mean=False):
         if ls.params is None:
             raise ValueError("must set parameter values to solve posterior")
         assert ls.solver is base.solver and ls.im is base.im, "snapshots must share the prior (clone_for_data)"
-    if base.ensemble_comm.rank != 0:
-        return
+    comm = base.ensemble_comm
+    shared = comm.size > 1 and bool(base.__dict__.get("_prior_shared", False))
+    if shared:
+        mine = [i for i in range(len(solvers)) if i % comm.size == comm.rank]
+    else:
+        mine = list(range(len(solvers))) if comm.rank == 0 else []
     sp, G, im, ctx = base.solver, base.G, base.im, base.solver.ctx
-    ns, n, nobs = len(solvers), sp.n, base.data.get_n_obs()
-    rhos = [float(np.exp(ls.params[0])) for ls in solvers]
+    n, nobs = sp.n, base.data.get_n_obs()
+    outs = {}
+    if mine:
+        sub = [solvers[i] for i in mine]
+        ns = len(sub)
+        rhos = [float(np.exp(ls.params[0])) for ls in sub]
+        sfs = [r if scale_mean else 1. for r in rhos]
 
-    def dense_cols(rho2s, with_Cu, rhs_cols):
-        out = ctx.empty((nobs, ns))
-        ctx.sync()                       # right-hand sides were produced on the main stream; clones may use their own
-        for s, ls in enumerate(solvers):
-            try:
-                col = ls._dense_solve(rho2s[s], with_Cu, rhs_cols[s])
-            except LinAlgError:
-                raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy" +
-                                  (" plus forcing covariance" if with_Cu else ""))
-            if ls.dctx is not ctx:
-                ls.dctx.sync()
-            out[:, s] = col
-        return out
+        def dense_cols(rho2s, with_Cu, rhs_cols):
+            out = ctx.empty((nobs, ns))
+            ctx.sync()                   # right-hand sides were produced on the main stream; clones may use their own
+            for s, ls in enumerate(sub):
+                try:
+                    col = ls._dense_solve(rho2s[s], with_Cu, rhs_cols[s])
+                except LinAlgError:
+                    raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy" +
+                                      (" plus forcing covariance" if with_Cu else ""))
+                if ls.dctx is not ctx:
+                    ls.dctx.sync()
+                out[:, s] = col
+            return out
 
-    def aga(M):      # A^-1 G A^-1 on a block of columns, Dirichlet lifting off (solving_utils.py:46-57)
-        X = ctx.empty((n, ns))
-        sp.solve_block(M, X)
-        Wb = G.G.matmul(X)
-        sp.solve_block(Wb, X)
-        return X
+        def aga(M):      # A^-1 G A^-1 on a block of columns, Dirichlet lifting off (solving_utils.py:46-57)
+            X = ctx.empty((n, ns))
+            sp.solve_block(M, X)
+            Wb = G.G.matmul(X)
+            sp.solve_block(Wb, X)
+            return X
 
-    T1 = dense_cols([0.] * ns, False, [ls._data_device()["data"] for ls in solvers])
-    M2 = aga(im.csr.matmul(T1))                                     # (n x ns)
-    M2 = M2 * torch.tensor(rhos, dtype=torch.float64, device=M2.device)[None, :] + base._x_dev[:, None]
-    D1 = im.csc.matmul(M2.contiguous())                             # (n_obs x ns)
-    D2 = dense_cols([r * r for r in rhos], True, [D1[:, s].contiguous() for s in range(ns)])
-    M3 = aga(im.csr.matmul(D2))
-    for s, (ls, x) in enumerate(zip(solvers, xs)):
-        sf = rhos[s] if scale_mean else 1.
-        out = sf * M2[:, s] - sf * rhos[s] ** 2 * M3[:, s]
-        xf = x.function if isinstance(x, fem.Vector) else x
-        xf.data[:] = out.cpu().numpy()
+        T1 = dense_cols([0.] * ns, False, [ls._data_device()["data"] for ls in sub])
+        M2 = aga(im.csr.matmul(T1))                                     # (n x ns)
+        M2 = M2 * torch.tensor(rhos, dtype=torch.float64, device=M2.device)[None, :] + base._x_dev[:, None]
+        D1 = im.csc.matmul(M2.contiguous())                             # (n_obs x ns)
+        D2 = dense_cols([r * r for r in rhos], True, [D1[:, s].contiguous() for s in range(ns)])
+        M3 = aga(im.csr.matmul(D2))
+        for s, i in enumerate(mine):
+            outs[i] = (sfs[s] * M2[:, s] - sfs[s] * rhos[s] ** 2 * M3[:, s]).contiguous()
+    for i, x in enumerate(xs):
+        owner = i % comm.size if shared else 0
+        if shared and owner != 0:       # bring the mean of a snapshot computed elsewhere to the root
+            if comm.rank == owner:
+                comm.send_tensor(outs[i], dst=0)
+            elif comm.rank == 0:
+                outs[i] = comm.recv_tensor(ctx.empty((n,)), src=owner)
+        if comm.rank == 0:
+            xf = x.function if isinstance(x, fem.Vector) else x
+            xf.data[:] = outs[i].cpu().numpy()

@@ -47,40 +47,77 @@ def fit_linear_solver(ls, start=None, **minimize_kwargs):
 
 def fit_snapshots(ls, datas, start=None, concurrent=True, **minimize_kwargs):
     """MAP fits for several data snapshots taken at the SAME sensors: the prior (x, mu, Cu) of ``ls`` is shared
-    (``LinearSolver.clone_for_data``) and, on a single process, every snapshot's L-BFGS-B loop runs in its own host
-    thread on its own CUDA stream, so that the latency-bound parts of one fit (Cholesky panels, small GEMMs) overlap
-    with the throughput-bound parts of the others.  Returns the list of fitted LinearSolvers (``ls`` itself is used
-    for ``datas[0]`` when that is its own data set).  Extension over the reference API."""
+    (``LinearSolver.clone_for_data``).  On one process every snapshot's L-BFGS-B loop runs in its own host thread on its
+    own CUDA stream, so that the latency-bound parts of one fit (Cholesky panels, small GEMMs) overlap with the
+    throughput-bound parts of the others.  On several processes (one per GPU) the prior is first broadcast to every
+    GPU (``share_prior``) and the snapshots are dealt out round-robin; the optima are exchanged at the end, so every
+    process returns the same list of fitted LinearSolvers.  Extension over the reference API."""
     import threading
     import torch
     if ls.Cu is None or ls.mu is None:
         ls.solve_prior()
     world = comm_world()
-    conc = bool(concurrent) and world.size == 1 and len(datas) > 1
+    ndata = len(datas)
+    if start is None:       # one common random start, as estimate_params_MAP draws it (estimation.py:83-88)
+        start = 5. * (np.random.random(3) - 0.5) if world.rank == 0 else None
+        start = world.bcast(start, root=0)
+    if world.size > 1:
+        ls.share_prior()
+    mine = [i for i in range(ndata) if i % world.size == world.rank]
+    conc = bool(concurrent) and len(mine) > 1
     solvers = []
-    for od in datas:
-        solvers.append(ls if (od is ls.data and not conc) else ls.clone_for_data(od, private_stream=conc))
-    if not conc:
-        for s in solvers:
-            fit_linear_solver(s, start=start, **minimize_kwargs)
-        return solvers
-    torch.cuda.synchronize()                  # the shared prior is complete before the side streams read it
-    errors = [None] * len(solvers)
+    for i, od in enumerate(datas):
+        own_stream = conc and i in mine
+        solvers.append(ls if (od is ls.data and not own_stream) else ls.clone_for_data(od, private_stream=own_stream))
+    for s in solvers:
+        s._local_eval = True          # every rank holds the prior: no per-evaluation broadcast
+    errors = [None] * ndata
+    results = np.zeros((ndata, 4))
 
-    def work(i):
+    def work(i, use_stream):
         try:
-            with torch.cuda.stream(solvers[i].dctx.tstream):
-                fit_linear_solver(solvers[i], start=start, **minimize_kwargs)
-                solvers[i].dctx.sync()
+            if use_stream:
+                with torch.cuda.stream(solvers[i].dctx.tstream):
+                    _minimize_local(solvers[i], start, minimize_kwargs)
+                    solvers[i].dctx.sync()
+            else:
+                _minimize_local(solvers[i], start, minimize_kwargs)
+            results[i, :3] = solvers[i].params
+            results[i, 3] = solvers[i].n_logpost_evals
         except BaseException as exc:      # re-raised in the caller
             errors[i] = exc
 
-    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(solvers))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    if conc:
+        torch.cuda.synchronize()              # the shared prior is complete before the side streams read it
+        threads = [threading.Thread(target=work, args=(i, True)) for i in mine]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    else:
+        for i in mine:
+            work(i, False)
+    failed = world.allreduce(float(any(e is not None for e in errors)))
     for exc in errors:
         if exc is not None:
             raise exc
+    assert not failed, "a MAP fit failed on another process"
+    if world.size > 1:
+        results = np.asarray(world.allreduce(results))        # rows owned by other ranks are zero here
+    for i, s in enumerate(solvers):
+        s.set_params(results[i, :3])
+        s.n_logpost_evals = int(results[i, 3])
+        s._local_eval = False
     return solvers
+
+
+def _minimize_local(ls, start, minimize_kwargs):
+    "the L-BFGS-B loop of fit_linear_solver without its cross-process checks (used per snapshot / per thread)"
+    ls.fuse_gradient = True
+    try:
+        fmin_dict = minimize(ls.logposterior, start, method='L-BFGS-B', jac=ls.logpost_deriv, options=minimize_kwargs)
+    finally:
+        ls.fuse_gradient = False
+    assert fmin_dict['success'], "minimization routine failed"
+    ls.set_params(fmin_dict['x'])
+    ls.minimize_result = fmin_dict

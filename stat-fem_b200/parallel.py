@@ -66,6 +66,19 @@ class EnsembleComm(object):
         out = t.cpu().numpy()
         return out.item() if out.ndim == 0 else out
 
+    def broadcast_tensor(self, t, root=0):
+        "in-place broadcast of a (device) tensor"
+        if self._dist is not None and self.size > 1:
+            self._dist.broadcast(t, src=root, group=self.group)
+        return t
+
+    def send_tensor(self, t, dst):
+        self._dist.send(t.contiguous(), dst=dst, group=self.group)
+
+    def recv_tensor(self, t, src):
+        self._dist.recv(t, src=src, group=self.group)
+        return t
+
     # ---- tensor collectives used by the sharded Cu assembly -------------------------------------------------
     def all_gather_rows(self, local, counts):
         """local: tensor (m x n_loc).  Returns a list of tensors (m x counts[s]) -- every rank's column block of the
@@ -82,6 +95,29 @@ class EnsembleComm(object):
             send[:, :local.shape[1]] = local
         outs = [torch.empty((m, cmax), dtype=local.dtype, device=local.device) for _ in counts]
         self._dist.all_gather(outs, send, group=self.group)
+        return [o[:, :int(cnt)] for o, cnt in zip(outs, counts)]
+
+    def all_gather_rows_start(self, local, counts):
+        "asynchronous all_gather_rows: returns a handle for all_gather_rows_finish (the exchange overlaps the caller's GEMM)"
+        if self._dist is None or self.size == 1:
+            return ([local], None, counts)
+        import torch
+        cmax = int(max(counts))
+        m = int(local.shape[0])
+        if int(local.shape[1]) == cmax:
+            send = local.contiguous()
+        else:
+            send = torch.zeros((m, cmax), dtype=local.dtype, device=local.device)
+            send[:, :local.shape[1]] = local
+        outs = [torch.empty((m, cmax), dtype=local.dtype, device=local.device) for _ in counts]
+        work = self._dist.all_gather(outs, send, group=self.group, async_op=True)
+        return (outs, work, counts, send)
+
+    def all_gather_rows_finish(self, handle):
+        outs, work, counts = handle[0], handle[1], handle[2]
+        if work is None:
+            return outs
+        work.wait()
         return [o[:, :int(cnt)] for o, cnt in zip(outs, counts)]
 
     def gather_rows_to_root(self, local, counts, root=0):

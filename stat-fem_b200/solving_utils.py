@@ -18,10 +18,11 @@ _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_si
 
 
 def _lattice_nodes(coords):
-    """level-1 lattice: 2^p cells per direction with a spacing of TWICE the estimated mesh width, anchored at the lower
-    corner of the bounding box and extended past the upper corner if necessary.  On lattice-like meshes every DOF then
-    sits on a lattice node, edge midpoint or cell centre, the transfer weights are exactly 0, 1/2, 1/4, 1, and all
-    Galerkin coarse operators stay compact (3^d points) instead of filling their 5^d stencils."""
+    """level-1 lattice: 2^p cells per direction.  Preferred: a spacing of exactly TWICE the estimated mesh width,
+    anchored at the lower corner of the bounding box and overhanging the upper corner (by at most 25 %): on lattice-like
+    meshes every DOF then sits on a lattice node, edge midpoint or cell centre, the transfer weights are exactly 0, 1/2,
+    1/4, 1, and all Galerkin coarse operators stay compact (3^d points) instead of filling their 5^d stencils.
+    Otherwise the lattice is stretched over the box with a spacing of 1.5 to 3 mesh widths."""
     n, d = coords.shape
     lo, hi = coords.min(axis=0), coords.max(axis=0)
     ext = np.where(hi > lo, hi - lo, 1.)
@@ -34,10 +35,16 @@ def _lattice_nodes(coords):
         cells = max(per_side * ext[k] / geo - 1., 2.)          # estimated number of mesh cells along direction k
         if abs(cells - round(cells)) < 1.e-6:
             cells = float(round(cells))
-        H = 2. * ext[k] / cells
-        p = max(int(np.ceil(np.log2(ext[k] / H) - 1.e-9)), 1)
-        m1.append(2 ** p + 1)
-        hi_lat.append(lo[k] + H * 2 ** p)
+        r = cells / 2.                                         # lattice cells of width two mesh cells
+        p_up = max(int(np.ceil(np.log2(r) - 1.e-9)), 1)
+        if 2. ** p_up / r - 1. <= 0.25:                        # aligned lattice, overhanging the box by at most 25 %
+            H = 2. * ext[k] / cells
+            m1.append(2 ** p_up + 1)
+            hi_lat.append(lo[k] + H * 2 ** p_up)
+        else:                                                  # stretched to the box: spacing in [1.5, 3) mesh widths
+            p = max(int(np.floor(np.log2(cells / 1.5) + 1.e-9)), 1)
+            m1.append(2 ** p + 1)
+            hi_lat.append(hi[k])
     return lo, np.array(hi_lat), m1
 
 
@@ -208,7 +215,7 @@ def solve_forcing_covariance(G, ls, rhs):
     return f.vector()
 
 
-def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_bytes=2.e9):
+def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_bytes=1.e9):
     """The exchange step of the sharded covariance assembly.  Rank r holds ``Wr`` (n x its columns of the right
     matrix) and ``Zl`` (n x its columns of the left matrix).  Row chunks of ``Zl`` are all-gathered and every rank
     accumulates its rows ``Wr^T Z_left`` of the (n_right x n_left) result with ``gemm_tn(W_chunk, Z_chunk, out, beta)``
@@ -224,9 +231,15 @@ def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_by
         return res
     lcounts = [ownership_range(n_left, s, size) for s in range(size)]
     chunk = max(1024, min(n, int(chunk_bytes / (8. * max(n_left, 1)))))
-    for k0 in range(0, n, chunk):
+    widths = [b - a for a, b in lcounts]
+    starts = list(range(0, n, chunk))
+    # double-buffered: the all-gather of row chunk i+1 (NCCL, its own stream) is in flight while chunk i is multiplied
+    handle = ensemble_comm.all_gather_rows_start(Zl[starts[0]:min(n, starts[0] + chunk), :], widths)
+    for i, k0 in enumerate(starts):
         k1 = min(n, k0 + chunk)
-        pieces = ensemble_comm.all_gather_rows(Zl[k0:k1, :], [b - a for a, b in lcounts])
+        pieces = ensemble_comm.all_gather_rows_finish(handle)
+        if i + 1 < len(starts):
+            handle = ensemble_comm.all_gather_rows_start(Zl[starts[i + 1]:min(n, starts[i + 1] + chunk), :], widths)
         for (a, b), piece in zip(lcounts, pieces):
             if nloc and b > a:
                 gemm_tn(Wr[k0:k1], piece, res[:, a:b], 1.0)
