@@ -66,15 +66,27 @@ def gpu_step(prob, comm, resident, stats=None):
     from stat_fem_b200 import fem
     from stat_fem_b200.estimation import fit_snapshots
     V, A, b = prob["V"], prob["A"], prob["b"]
+    _t = [time.perf_counter()]
+
+    def lap(name):       # SFEM_BENCH_TIMING=1: wall-clock phase report (adds device synchronisations)
+        if os.environ.get("SFEM_BENCH_TIMING") and comm.rank == 0:
+            import torch
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            print("    [%s] %-26s %.3f s" % ("resident" if resident else "e2e", name, now - _t[0]), file=sys.stderr, flush=True)
+            _t[0] = now
     G = stat_fem.ForcingCovariance(V, prob["sigma_f"], prob["l_f"], prob["cutoff"], prob["reg"])
     G.assemble()
+    lap("G assemble")
     ods = [stat_fem.ObsData(prob["sensors"], y, prob["unc"]) for y in prob["datas"]]
     ls = stat_fem.LinearSolver(A, b, G, ods[0], ensemble_comm=comm)
     if resident and "im" in prob:
         ls.im = prob["im"]              # interpolation matrix already assembled and resident in HBM
         ls._owns_im = False
     ls.host_results = not resident
+    lap("LinearSolver + MG setup")
     mu, Cu = ls.solve_prior()
+    lap("solve_prior")
     out = dict(nnzG=G.G.nnz, iters=list(ls.solver.block_iterations), thetas=[], evals=0)
     # the snapshots share the sensors, hence the prior: their MAP fits run concurrently (one stream each) and their
     # posterior means are advanced together as block solves
@@ -82,8 +94,10 @@ def gpu_step(prob, comm, resident, stats=None):
     for lss in solvers:
         out["thetas"].append(lss.params.copy())
         out["evals"] += lss.n_logpost_evals
+    lap("MAP fits")
     xs = [fem.Function(V) for _ in ods]
     stat_fem.solve_posterior_snapshots(solvers, xs, scale_mean=True)
+    lap("posterior means")
     out["mu0"] = float(mu[0]) if len(mu) else 0.
     out["cu_checksum"] = float(Cu.sum()) if comm.rank == 0 else 0.       # same value at every N: the sharded path is exact
     out["x_norm"] = float(np.linalg.norm(xs[-1].data))

@@ -74,7 +74,7 @@ class LinearSolver(object):
         other.params = None
         other._cache = None
         other._dense_work = None if private_stream else self._dense_work
-        other._dense_ctx = _lib.new_stream_context() if private_stream else self.__dict__.get("_dense_ctx")
+        other._dense_ctx = _lib.acquire_stream_context() if private_stream else self.__dict__.get("_dense_ctx")
         other._owns_dense_ctx = bool(private_stream)
         other._data_dev = None
         other.n_logpost_evals = 0
@@ -101,7 +101,7 @@ class LinearSolver(object):
                 self.im.destroy()
             if self.__dict__.get("_owns_dense_ctx", False):
                 self._dense_work = None
-                _lib.destroy_context(self._dense_ctx)
+                _lib.release_stream_context(self._dense_ctx)      # back to the pool, workspace attached
         except Exception:
             pass
 
@@ -120,7 +120,11 @@ class LinearSolver(object):
         n = self.data.get_n_obs()
         need = _lib.lib().sfem_dense_workspace_bytes(n)
         if self._dense_work is None or self._dense_work.numel() < need + 256:
-            self._dense_work = self.dctx.workspace(need)
+            pooled = self.dctx.__dict__.get("_work_cache")         # a pooled stream context keeps its workspace
+            if pooled is None or pooled.numel() < need + 256:
+                pooled = self.dctx.workspace(need)
+                self.dctx._work_cache = pooled
+            self._dense_work = pooled
         w = self._dense_work
         off = (-w.data_ptr()) % 256
         return C.c_void_p(w.data_ptr() + off), int(w.numel() - off)

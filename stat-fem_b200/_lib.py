@@ -217,6 +217,25 @@ def new_context(device=None):
     return Context(device)
 
 
+_stream_pool = {}
+
+
+def acquire_stream_context(device=None):
+    """a stream context from a per-device pool (created on demand).  Pooling keeps the CUDA streams, the library's
+    temporaries and the torch allocations made on those streams alive between uses: torch's caching allocator keeps one
+    pool of blocks per stream, so fresh streams every time would mean fresh cudaMallocs (and synchronising cudaFrees
+    under memory pressure) every time."""
+    torch = torch_mod()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    free = _stream_pool.setdefault(dev, [])
+    return free.pop() if free else new_stream_context(dev)
+
+
+def release_stream_context(ctx):
+    if ctx is not None and ctx.handle:
+        _stream_pool.setdefault(ctx.device, []).append(ctx)
+
+
 def new_stream_context(device=None):
     """a private context on its OWN CUDA stream: independent dense work (e.g. the MAP fits of several data snapshots)
     submitted from different host threads overlaps on the GPU.  Callers make that stream current in their thread
