@@ -294,24 +294,8 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
         const bool ok0 = col < a.k, ok1 = (VEC == 2) && (col + 1 < a.k);
         double* Yc = a.Y + col;
 
-        for (int r = wsub; r < nr; r += sstride) {
-            const unsigned short* ec = ecols + r * W;
-            const double* ev = evals + r * W;
-            double acc0 = 0.0, acc1 = 0.0;
-            for (int w = 0; w < W; w += 2) {
-                const unsigned cc = *reinterpret_cast<const unsigned*>(ec + w);
-                const double2 vv = *reinterpret_cast<const double2*>(ev + w);
-                const double* xa = xs + (cc & 0xffffu) * SW;
-                const double* xb = xs + (cc >> 16) * SW;
-                if (VEC == 2) {
-                    const double2 ta = *reinterpret_cast<const double2*>(xa), tb = *reinterpret_cast<const double2*>(xb);
-                    acc0 = fma(vv.x, ta.x, acc0); acc1 = fma(vv.x, ta.y, acc1);
-                    acc0 = fma(vv.y, tb.x, acc0); acc1 = fma(vv.y, tb.y, acc1);
-                } else {
-                    acc0 = fma(vv.x, xa[0], acc0);
-                    acc0 = fma(vv.y, xb[0], acc0);
-                }
-            }
+        // epilogue of one row: fuses the caller's vector work and streams the result row out
+        auto finish_row = [&](int r, double acc0, double acc1) {
             double s0 = 0.0, s1 = 0.0;
             if (NEED_SELF) {
                 const unsigned sl = sself[r];
@@ -342,6 +326,40 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
                 if (MODE == TM_JACOBI_DOT) { d0 = fma(b0, y0, d0); d1 = fma(b1, y1, d1); }
             }
             stv<VEC>(Yc + (int64_t)(r0 + r) * a.ldy, ok0, ok1, y0, y1);
+        };
+        // two rows per pass and per lane group: twice the independent shared-memory -> DFMA chains in flight
+        for (int r = wsub; r < nr; r += 2 * sstride) {
+            const int rb = r + sstride;
+            const bool two = rb < nr;
+            const unsigned short* eca = ecols + r * W;
+            const double* eva = evals + r * W;
+            const unsigned short* ecb = ecols + (two ? rb : r) * W;
+            const double* evb = evals + (two ? rb : r) * W;
+            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+            for (int w = 0; w < W; w += 2) {
+                const unsigned ca = *reinterpret_cast<const unsigned*>(eca + w);
+                const unsigned cb2 = *reinterpret_cast<const unsigned*>(ecb + w);
+                const double2 va = *reinterpret_cast<const double2*>(eva + w);
+                const double2 vb = *reinterpret_cast<const double2*>(evb + w);
+                const double* xa0 = xs + (ca & 0xffffu) * SW;
+                const double* xa1 = xs + (ca >> 16) * SW;
+                const double* xb0 = xs + (cb2 & 0xffffu) * SW;
+                const double* xb1 = xs + (cb2 >> 16) * SW;
+                if (VEC == 2) {
+                    const double2 ta0 = *reinterpret_cast<const double2*>(xa0), ta1 = *reinterpret_cast<const double2*>(xa1);
+                    const double2 tb0 = *reinterpret_cast<const double2*>(xb0), tb1 = *reinterpret_cast<const double2*>(xb1);
+                    a0 = fma(va.x, ta0.x, a0); a1 = fma(va.x, ta0.y, a1);
+                    c0 = fma(vb.x, tb0.x, c0); c1 = fma(vb.x, tb0.y, c1);
+                    a0 = fma(va.y, ta1.x, a0); a1 = fma(va.y, ta1.y, a1);
+                    c0 = fma(vb.y, tb1.x, c0); c1 = fma(vb.y, tb1.y, c1);
+                } else {
+                    a0 = fma(va.x, xa0[0], a0); c0 = fma(vb.x, xb0[0], c0);
+                    a0 = fma(va.y, xa1[0], a0); c0 = fma(vb.y, xb1[0], c0);
+                }
+            }
+            finish_row(r, a0, a1);
+            if (two) finish_row(rb, c0, c1);
         }
         const bool slab_done = HAS_DOT && ((t + 1) % nmine == 0);
         if (slab_done) {
