@@ -245,6 +245,69 @@ __global__ void __launch_bounds__(RB_THREADS) cg_scatter_perm_kernel(int64_t n, 
     }
 }
 
+// tile path: x += alpha p (the deferred update of the previous iteration), then p = z + beta p  -- one pass over p
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) cg_pxupdate_kernel(int64_t n, int k, const double* __restrict__ alpha,
+                                                                const double* __restrict__ beta, const double* __restrict__ Z,
+                                                                double* __restrict__ P, double* __restrict__ X,
+                                                                int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    double al0 = L.ok0 ? alpha[L.c] : 0.0, al1 = L.ok1 ? alpha[L.c + 1] : 0.0;
+    double be0 = L.ok0 ? beta[L.c] : 0.0, be1 = L.ok1 ? beta[L.c + 1] : 0.0;
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double z0, z1, p0, p1, x0, x1;
+        ld_cols<VEC>(Z + row * k, L, z0, z1);
+        ld_cols<VEC>(P + row * k, L, p0, p1);
+        ld_cols<VEC>(X + row * k, L, x0, x1);
+        st_cols<VEC>(X + row * k, L, fma(al0, p0, x0), fma(al1, p1, x1));
+        st_cols<VEC>(P + row * k, L, fma(be0, p0, z0), fma(be1, p1, z1));
+    }
+}
+
+// tile path: r -= alpha q ; partial rr = sum r^2
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) cg_rupdate_kernel(int64_t n, int k, const double* __restrict__ alpha,
+                                                               const double* __restrict__ Q, double* __restrict__ R,
+                                                               double* __restrict__ part_rr, int64_t rows_per_block) {
+    __shared__ double red[RB_WARPS][64];
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    double al0 = L.ok0 ? alpha[L.c] : 0.0, al1 = L.ok1 ? alpha[L.c + 1] : 0.0;
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    double s0 = 0, s1 = 0;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double q0, q1, a0, a1;
+        ld_cols<VEC>(Q + row * k, L, q0, q1);
+        ld_cols<VEC>(R + row * k, L, a0, a1);
+        a0 -= al0 * q0; a1 -= al1 * q1;
+        st_cols<VEC>(R + row * k, L, a0, a1);
+        s0 += a0 * a0; s1 += a1 * a1;
+    }
+    block_partials<VEC>(s0, s1, L, k, part_rr, red);
+}
+
+// x += alpha p (final deferred update)
+template <int VEC>
+__global__ void __launch_bounds__(RB_THREADS) cg_xupdate_kernel(int64_t n, int k, const double* __restrict__ alpha,
+                                                               const double* __restrict__ P, double* __restrict__ X,
+                                                               int64_t rows_per_block) {
+    const int warp = threadIdx.x >> 5;
+    LaneCols<VEC> L(k);
+    double al0 = L.ok0 ? alpha[L.c] : 0.0, al1 = L.ok1 ? alpha[L.c + 1] : 0.0;
+    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
+        double p0, p1, x0, x1;
+        ld_cols<VEC>(P + row * k, L, p0, p1);
+        ld_cols<VEC>(X + row * k, L, x0, x1);
+        st_cols<VEC>(X + row * k, L, fma(al0, p0, x0), fma(al1, p1, x1));
+    }
+}
+
 // out[c] = sum_b part[b][c], b ascending within 8 interleaved lanes, then the 8 lane sums in order (deterministic)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(int nparts, int k, const double* __restrict__ part, double* __restrict__ out) {
     __shared__ double sh[8][33];
@@ -349,12 +412,8 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
     int it = 0;
     int nact = *h_nact;
     while (nact > 0 && it < max_it) {
-        {   // p = z + beta p   (beta = 0 on the first pass: p was zeroed)
-            ProfScope _ps(c, TAG_CG_VEC, 3 * 8.0 * (double)n * k, 0.0);
-            if (v2) cg_pupdate_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.beta, Z, nullptr, Pa, g.rows_per_block);
-            else cg_pupdate_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.beta, Z, nullptr, Pa, g.rows_per_block);
-            KCHECK(c);
-        }
+        // x += alpha_prev p_prev (alpha = beta = 0 and p = 0 on the first pass), p = z + beta p
+        LAUNCH_T(5, cg_pxupdate_kernel, n, k, s.alpha, s.beta, Z, Pa, Xq, g.rows_per_block);
         {   // q = A p ; sigma = p.q
             TileArgs a; a.k = k; a.X = Pa; a.ldx = k; a.Y = Q; a.ldy = k; a.partials = part_tile;
             rc = tileop_apply(c, TAG_CSR_MULT, L0->tA, TM_MULT_DOT, a,
@@ -365,12 +424,7 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         KCHECK(c);
         cg_alpha_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, s);
         KCHECK(c);
-        {
-            ProfScope _ps(c, TAG_CG_VEC, 6 * 8.0 * (double)n * k, 0.0);
-            if (v2) cg_update_kernel<2, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, Pa, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
-            else cg_update_kernel<1, false><<<grid, RB_THREADS, 0, c->stream>>>(n, k, s.alpha, Pa, Q, Xq, k, R, nullptr, part1, nullptr, g.rows_per_block);
-            KCHECK(c);
-        }
+        LAUNCH_T(3, cg_rupdate_kernel, n, k, s.alpha, Q, R, part1, g.rows_per_block);     // x is updated with the next direction
         rc = mg_apply_tiles(c, k, R, Z, Q, Pb, mgwork, part_tile, &nch);      // Q is free again after the update
         if (rc) return rc;
         reduce_partials_kernel<<<rb, 256, 0, c->stream>>>(nch, k, part_tile, red + kk);
@@ -386,6 +440,7 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         ++it;
     }
     if (iters_out) *iters_out = it;
+    if (it > 0) LAUNCH_T(3, cg_xupdate_kernel, n, k, s.alpha, Pa, Xq, g.rows_per_block);     // the last deferred update
     LAUNCH_T(2, cg_scatter_perm_kernel, n, k, perm, Xq, X, ldx, g.rows_per_block);
     {   // true residual || B - A X || / || B || per column, in the caller's numbering
         rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, X, ldx, R, k, B, ldb);
