@@ -106,6 +106,16 @@ __global__ void lat_chunk_kernel(TileGeom g, int nchunks, int64_t n, int* __rest
     chunk_ptr[cidx] = (int)g.tile_offset(t0, t1, t2);
 }
 
+// split every chunk into `parts` pieces of at most `sub` consecutive rows (trailing pieces may be empty)
+__global__ void refine_chunks_kernel(int nchunks, int sub, int parts, const int* __restrict__ in, int* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nchunks * parts) return;
+    if (t == nchunks * parts) { out[t] = in[nchunks]; return; }
+    int cidx = t / parts, p = t - cidx * parts;
+    int v = in[cidx] + p * sub;
+    out[t] = v < in[cidx + 1] ? v : in[cidx + 1];
+}
+
 __global__ void permute_vector_kernel(int64_t n, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < n) out[q] = in[perm ? perm[q] : q];
@@ -407,6 +417,22 @@ int mg_build_tiles(sfem_ctx* c) {
                                                                                c->mg_omega2 / c->mg_omega, L->dinv_t2);
         c->launches++;
     }
+    // restrictions gather ~5 input rows per output row: their chunks are the level's chunks split into pieces of 8
+    // rows, which keeps the staged working set (and with it the number of resident CTAs) like that of the other operators
+    auto build_restriction = [&](auto gen, int l_rows, int64_t nrows, int64_t ncols, TileOp* out) -> int {
+        const int sub = 8;
+        int parts = (max_rows[l_rows] + sub - 1) / sub;
+        if (parts <= 1) return build_op(c, gen, nrows, ncols, chunk_ptr[l_rows], nchunks[l_rows], max_rows[l_rows], out);
+        int* fine = nullptr;
+        int nf = nchunks[l_rows] * parts;
+        if (cudaMalloc(&fine, sizeof(int) * ((size_t)nf + 1)) != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: out of memory");
+        refine_chunks_kernel<<<(nf + 256) / 256, 256, 0, c->stream>>>(nchunks[l_rows], sub, parts, chunk_ptr[l_rows], fine);
+        c->launches++;
+        int r = build_op(c, gen, nrows, ncols, fine, nf, sub, out);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(fine);
+        return r;
+    };
     // ---- operators
     {
         GenA0 g{c->A_ptr, c->A_idx, c->A_val, L0->perm, L0->iperm};
@@ -419,7 +445,7 @@ int mg_build_tiles(sfem_ctx* c) {
         GenP0 gp{lat1, d, L0->perm, L0->cidx, L0->frac, L0->constrained, L1->constrained, L1->iperm};
         TRY_RC(build_op(c, gp, n, L1->n, chunk_ptr[0], nchunks[0], max_rows[0], &L0->tP));
         GenR0 gr{lat1, d, L1->perm, L0->cell_start, L0->cell_nodes, L0->frac, L0->constrained, L1->constrained, L0->iperm};
-        TRY_RC(build_op(c, gr, L1->n, n, chunk_ptr[1], nchunks[1], max_rows[1], &L0->tR));
+        TRY_RC(build_restriction(gr, 1, L1->n, n, &L0->tR));
     }
     for (int l = 1; l < nl; ++l) {
         MGLevel* L = c->mg[l];
@@ -436,7 +462,7 @@ int mg_build_tiles(sfem_ctx* c) {
             GenLatP gp{P, L->perm, C->iperm, L->constrained, C->constrained};
             TRY_RC(build_op(c, gp, L->n, C->n, chunk_ptr[l], nchunks[l], max_rows[l], &L->tP));
             GenLatR gr{P, C->perm, L->iperm, L->constrained, C->constrained};
-            TRY_RC(build_op(c, gr, C->n, L->n, chunk_ptr[l + 1], nchunks[l + 1], max_rows[l + 1], &L->tR));
+            TRY_RC(build_restriction(gr, l + 1, C->n, L->n, &L->tR));
         }
     }
     cudaStreamSynchronize(c->stream);

@@ -37,7 +37,9 @@ def _lattice_nodes(coords):
             cells = float(round(cells))
         r = cells / 2.                                         # lattice cells of width two mesh cells
         p_up = max(int(np.ceil(np.log2(r) - 1.e-9)), 1)
-        if 2. ** p_up / r - 1. <= 0.25:                        # aligned lattice, overhanging the box by at most 25 %
+        # aligned lattice if it overhangs the box by at most 25 % (60 % in 3-D, where a stretched lattice costs 5^3-point
+        # coarse stencils instead of 3^3)
+        if 2. ** p_up / r - 1. <= (0.25 if d <= 2 else 0.6):
             H = 2. * ext[k] / cells
             m1.append(2 ** p_up + 1)
             hi_lat.append(lo[k] + H * 2 ** p_up)
