@@ -189,8 +189,11 @@ __device__ __forceinline__ void cp8(void* smem_dst, const void* __restrict__ src
 // CW lanes share one row (each owning VEC adjacent columns); a warp instruction covers 32 / CW rows.
 // Work items of a CTA: for each column slab, its chunks blockIdx.x + j * gridDim.x  (slab-major, so the per-lane dot
 // accumulators run over all chunks of a slab and are reduced once per slab).
-template <int CW, int VEC, int MODE>
-__global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
+// BREG: the right-hand-side rows of the next work item are prefetched into REGISTERS one pipeline step ahead (each lane
+// group owns at most 4 rows of a chunk) instead of being staged in shared memory: a third less shared memory per
+// stage (more resident CTAs) and two fewer shared-memory passes per row.
+template <int CW, int VEC, int MODE, bool BREG>
+__global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(TileDev op, TileArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int SW = CW * VEC;
     constexpr int SWB = SW * 8;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
         for (int r = wsub; r < nown; r += sstride) cp_row<VEC>(xs_a + (unsigned)(own + r) * SWB, Xc + (int64_t)(r0 + r) * ldx, bytes);
         for (int ss = wsub; ss < own; ss += sstride) cp_row<VEC>(xs_a + (unsigned)ss * SWB, Xc + (int64_t)need[ss] * ldx, bytes);
         for (int ss = own + nown + wsub; ss < nneed; ss += sstride) cp_row<VEC>(xs_a + (unsigned)ss * SWB, Xc + (int64_t)need[ss] * ldx, bytes);
-        if (HAS_B) {
+        if (HAS_B && !BREG) {
             const unsigned bs_a = xs_a + op.off_bs;
             const double* Bc = ((MODE == TM_MULT_ADD) ? a.Y : a.B) + col;
             const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
@@ -270,10 +273,38 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
     issue_item(0);
     asm volatile("cp.async.commit_group;\n" ::);
 
+    // register prefetch of the right-hand-side rows (BREG): rows wsub + q * sstride, q < 4, of work item t
+    double bn0[4] = {0.0, 0.0, 0.0, 0.0}, bn1[4] = {0.0, 0.0, 0.0, 0.0};
+    auto prefetch_b = [&](int t) {
+        if (!(HAS_B && BREG) || t >= T) return;
+        const int slab = t / nmine;
+        const int* dsc = reinterpret_cast<const int*>(cb0 + (size_t)(t & 3) * op.cb_bytes);
+        const int r0 = dsc[0], nr = dsc[1];
+        const int col = slab * SW + cl * VEC;
+        const bool ok0 = col < a.k, ok1 = (VEC == 2) && (col + 1 < a.k);
+        const double* Bc = ((MODE == TM_MULT_ADD) ? a.Y : a.B) + col;
+        const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = wsub + q * sstride;
+            bn0[q] = bn1[q] = 0.0;
+            if (r < nr) {
+                const double* p = Bc + (int64_t)(r0 + r) * lds;
+                if (VEC == 2 && ok1) { const double2 v = *reinterpret_cast<const double2*>(p); bn0[q] = v.x; bn1[q] = v.y; }
+                else if (ok0) bn0[q] = p[0];
+            }
+        }
+    };
+    prefetch_b(0);
+
     double d0 = 0.0, d1 = 0.0;
     for (int t = 0; t < T; ++t) {
+        double bc0[4], bc1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { bc0[q] = bn0[q]; bc1[q] = bn1[q]; }
         // requests of the next work item and the chunk record three items ahead (its buffer was last read by item t-1)
         issue_item(t + 1);
+        prefetch_b(t + 1);
         issue_record(t + 3);
         asm volatile("cp.async.commit_group;\n" ::);
         asm volatile("cp.async.wait_group 1;\n" ::);
@@ -295,7 +326,7 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
         double* Yc = a.Y + col;
 
         // epilogue of one row: fuses the caller's vector work and streams the result row out
-        auto finish_row = [&](int r, double acc0, double acc1) {
+        auto finish_row = [&](int r, double acc0, double acc1, double br0, double br1) {
             double s0 = 0.0, s1 = 0.0;
             if (NEED_SELF) {
                 const unsigned sl = sself[r];
@@ -305,8 +336,8 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
                     if (VEC == 2) s1 = xp[1];
                 }
             }
-            double b0 = 0.0, b1 = 0.0;
-            if (HAS_B) {
+            double b0 = br0, b1 = br1;
+            if (HAS_B && !BREG) {
                 const double* bp = bs + r * SW;
                 b0 = bp[0];
                 if (VEC == 2) b1 = bp[1];
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
             stv<VEC>(Yc + (int64_t)(r0 + r) * a.ldy, ok0, ok1, y0, y1);
         };
         // two rows per pass and per lane group: twice the independent shared-memory -> DFMA chains in flight
-        for (int r = wsub; r < nr; r += 2 * sstride) {
+        auto two_rows = [&](int r, double ba0, double ba1, double bb0, double bb1) {
             const int rb = r + sstride;
             const bool two = rb < nr;
             const unsigned short* eca = ecols + r * W;
@@ -358,8 +389,14 @@ __global__ void __launch_bounds__(512) tileop_kernel(TileDev op, TileArgs a) {
                     a0 = fma(va.y, xa1[0], a0); c0 = fma(vb.y, xb1[0], c0);
                 }
             }
-            finish_row(r, a0, a1);
-            if (two) finish_row(rb, c0, c1);
+            finish_row(r, a0, a1, ba0, ba1);
+            if (two) finish_row(rb, c0, c1, bb0, bb1);
+        };
+        if (BREG) {      // at most 4 rows per lane group: two passes with compile-time register indices
+            if (wsub < nr) two_rows(wsub, bc0[0], bc1[0], bc0[1], bc1[1]);
+            if (wsub + 2 * sstride < nr) two_rows(wsub + 2 * sstride, bc0[2], bc1[2], bc0[3], bc1[3]);
+        } else {
+            for (int r = wsub; r < nr; r += 2 * sstride) two_rows(r, 0.0, 0.0, 0.0, 0.0);
         }
         const bool slab_done = HAS_DOT && ((t + 1) % nmine == 0);
         if (slab_done) {
@@ -439,14 +476,14 @@ __global__ void __launch_bounds__(256) tileop_direct_kernel(TileDev op, TileArgs
 inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory geometry for one (operator, mode, slab width); returns the total bytes
-size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d) {
+size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d, bool breg = false) {
     bool has_b = (mode == TM_JACOBI || mode == TM_JACOBI_DOT || mode == TM_RESID || mode == TM_MULT_ADD);
     bool has_d = (mode == TM_JACOBI || mode == TM_JACOBI_DOT || mode == TM_PRESMOOTH2);
     bool has_dot = (mode == TM_MULT_DOT || mode == TM_JACOBI_DOT);
     size_t cb = (size_t)op.dl * 4 + (size_t)op.n4 * 4 + (size_t)op.e8 * 2 + (size_t)op.e8 * 8;
     size_t st = al16((size_t)op.max_need * SW * sizeof(double));
     size_t o_bs = st;
-    if (has_b) st += al16((size_t)op.max_rows * SW * sizeof(double));
+    if (has_b && !breg) st += al16((size_t)op.max_rows * SW * sizeof(double));
     size_t o_dr = st;
     if (has_d) st += al16((size_t)op.max_rows * sizeof(double) * (mode == TM_PRESMOOTH2 ? 2 : 1));
     size_t tot = 4 * cb + 2 * st;
@@ -459,27 +496,35 @@ size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d) {
 constexpr size_t SMEM_RESERVED = 1024;                    // per-CTA reservation of the hardware
 constexpr size_t SMEM_CAP = 227 * 1024 - SMEM_RESERVED;   // per-CTA dynamic limit
 
-template <int CW, int VEC, int MODE>
-int launch_variant(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int* nparts) {
+template <int CW, int VEC, int MODE, bool BREG>
+int launch_kernel(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int* nparts) {
     constexpr int SW = CW * VEC;
-    size_t smem = tile_layout(op, MODE, SW, &d);
+    size_t smem = tile_layout(op, MODE, SW, &d, BREG);
     if (smem > SMEM_CAP) return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: chunk working set (%zu bytes) exceeds shared memory", smem);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tileop_kernel<CW, VEC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        cudaFuncSetAttribute(tileop_kernel<CW, VEC, MODE, BREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         attr_set = true;
     }
     // persistent grid: as many CTAs as fit on the machine (8 warps each; one 16-warp CTA per SM if only one fits)
     int per_sm = (int)((227 * 1024) / (smem + SMEM_RESERVED));
     int threads = 256;
-    if (per_sm < 2) { per_sm = 1; threads = 512; }
+    if (per_sm < 2) { per_sm = 1; threads = BREG ? 256 : 512; }
     if (per_sm > TILE_MAX_CTAS_PER_SM) per_sm = TILE_MAX_CTAS_PER_SM;
     int64_t items = (int64_t)op.nchunks;
     int grid = (int)(items < (int64_t)per_sm * SFEM_NUM_SMS ? items : (int64_t)per_sm * SFEM_NUM_SMS);
     if (nparts) *nparts = grid;
-    tileop_kernel<CW, VEC, MODE><<<grid, threads, smem, c->stream>>>(d, a);
+    tileop_kernel<CW, VEC, MODE, BREG><<<grid, threads, smem, c->stream>>>(d, a);
     KCHECK(c);
     return SFEM_OK;
+}
+
+template <int CW, int VEC, int MODE>
+int launch_variant(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs& a, int* nparts) {
+    constexpr bool has_b = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
+    // register prefetch of the right-hand side needs at most 4 rows per lane group with 8 warps per CTA
+    if (has_b && op.max_rows <= 4 * 8 * (32 / CW) && c->tile_sw != 33) return launch_kernel<CW, VEC, MODE, true>(c, op, d, a, nparts);
+    return launch_kernel<CW, VEC, MODE, false>(c, op, d, a, nparts);
 }
 
 template <int MODE>
