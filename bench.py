@@ -113,6 +113,15 @@ def gpu_step(prob, comm, resident, stats=None):
     return out
 
 
+def workload_text(prob, nnz_per_row=None):
+    "the same description of the workload on both arms"
+    g = "G cutoff 1e-3" + (" (%.1f nnz/row)" % nnz_per_row if nnz_per_row is not None else "")
+    return ("%s: %dD Poisson, %d^%d P1 nodes (%d DOF), %d observations, %d snapshots, %s; step = G assembly + MG setup + "
+            "%d-column PCG solve + W=GZ + Cu=W^T Z + mean + %d x (MAP + posterior mean)" %
+            (prob["name"], prob["dim"], prob["nodes"], prob["dim"], prob["V"].dim(), prob["nobs"], prob["nsnap"], g,
+             prob["nobs"], prob["nsnap"]))
+
+
 def bytes_h2d(prob):
     V, A = prob["V"], prob["A"]
     n, d = V.coords.shape
@@ -264,11 +273,7 @@ def run_gpu(args):
         "metric": "time-to-posterior (s)", "value": dev_s / args.steps, "unit": "s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %dD Poisson, %d^%d P1 nodes (%d DOF), %d observations, %d snapshots, G cutoff 1e-3 "
-                               "(%.1f nnz/row); step = G assembly + MG setup + %d-column PCG solve + W=GZ + Cu=W^T Z + mean + "
-                               "%d x (MAP + posterior mean)" % (prob["name"], prob["dim"], prob["nodes"], prob["dim"], prob["V"].dim(),
-                                                                 prob["nobs"], prob["nsnap"], res["nnzG"] / prob["V"].dim(),
-                                                                 prob["nobs"], prob["nsnap"]),
+        "config": {"workload": workload_text(prob, res["nnzG"] / prob["V"].dim()),
                    "parallelism": "observation columns sharded over %d GPU(s)" % world,
                    "l2": "working set (>= %.1f GB per vector block) exceeds the 126 MB L2; no flush needed" %
                          (8e-9 * prob["V"].dim() * min(prob["nobs"], 384)),
@@ -431,8 +436,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "time-to-posterior (s)", "value": val, "unit": "s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %dD Poisson %d^%d nodes, %d observations, %d snapshots (CPU: extrapolated from a bounded sample)"
-                                   % (prob["name"], prob["dim"], prob["nodes"], prob["dim"], prob["nobs"], prob["nsnap"])},
+            "config": {"workload": workload_text(prob), "parallelism": "reference algorithm (oracle port) on %d host cores; each step = a bounded sample, extrapolated linearly to the full workload" % last["cores"]},
             "cpu_baseline": last, "gpu_launches": 0,
             "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
