@@ -83,6 +83,9 @@ int sfem_destroy(sfem_ctx* c) {
     if (c->A_dinv) cudaFree(c->A_dinv);
     if (c->scratch) cudaFree(c->scratch);
     if (c->dense_tmp) cudaFree(c->dense_tmp);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_aux) cudaEventDestroy(c->ev_aux);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
     return SFEM_OK;

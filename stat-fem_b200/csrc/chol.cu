@@ -23,6 +23,14 @@ constexpr int NB = 128;
 //   (iii) all warps apply the symmetric rank-32 update to the trailing lower triangle with DMMA 8x8x4 tiles.
 // Phase 2: inv(L) in place, by 32x32 blocks:  M_kj = L_kj inv(D_j)  (one sweep), then block columns right to left,
 // rows bottom to top:  X_ij = - sum_{k=j+1..i} X_ik M_kj  (DMMA), which only reads not-yet-overwritten blocks.
+// diagnostic (build with -DSFEM_PANEL_CLOCKS, read with tools/panel_clocks.py): cycle stamps of the phases of the last panel
+__device__ long long g_panel_clk[16];
+#ifdef SFEM_PANEL_CLOCKS
+#define PCLK(i) do { if (threadIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
+
 constexpr int PLD = 132;       // row stride of the panel in shared memory
 constexpr int DLD = 36;        // row stride of the 32x32 inverse diagonal blocks
 constexpr int SB = 32;         // sub-block width
@@ -40,17 +48,30 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
     double* rd = Dv + 4 * SB * DLD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lk = lane & 3;
-    for (int t = tid; t < NB * NB; t += 256) {
-        int r = t >> 7, cidx = t & (NB - 1);
-        double v = (r == cidx) ? 1.0 : 0.0;
-        if (r < nb && cidx <= r) v = A[(int64_t)r * lda + cidx];
-        s[r * PLD + cidx] = v;
+    PCLK(0);
+    // load the lower triangle: 8 independent loads in flight per thread (each row is a coalesced segment)
+    for (int t0 = tid; t0 < NB * NB; t0 += 256 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int t = t0 + u * 256;
+            int r = t >> 7, cidx = t & (NB - 1);
+            v[u] = (r == cidx) ? 1.0 : 0.0;
+            if (r < nb && cidx <= r) v[u] = A[(int64_t)r * lda + cidx];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int t = t0 + u * 256;
+            s[(t >> 7) * PLD + (t & (NB - 1))] = v[u];
+        }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 1: Cholesky by 32-wide block steps
+    PCLK(1);
     for (int jb = 0; jb < NB / SB; ++jb) {
         const int c0 = jb * SB, c1 = c0 + SB;
+        if (jb == 0) PCLK(2);
         double rinvs[SB];
         if (warp == 0) {
             double a[SB];
@@ -64,8 +85,14 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                     if (lane == 0 && *info == 0) *info = j0 + c0 + j + 1;
                     d = 1.0;
                 }
-                double rinv = rsqrt(d);
-                rinv = rinv * fma(-0.5 * d * rinv, rinv, 1.5);       // one Newton step: relative error ~1e-32 -> rounds like 1/sqrt
+                // hardware seed (relative error 2^-22) + two Newton steps: ~1 ulp, no range checks on the critical chain
+                double rinv;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(d));
+                {
+                    const double hd = 0.5 * d;
+                    rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
+                    rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
+                }
                 rinvs[j] = rinv;
                 double lij = a[j] * rinv;
                 if (lane == j) { lij = d * rinv; rd[c0 + j] = rinv; }
@@ -82,6 +109,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 if (k <= lane) roww[k] = a[k];
         }
         __syncthreads();
+        if (jb == 0) PCLK(3);
         if (warp == 0) {
             // (ii) inverse of the diagonal block: lane = column
             double x[SB];
@@ -120,6 +148,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
             }
         }
         __syncthreads();
+        if (jb == 0) PCLK(4);
         // (iii) trailing update of the lower triangle, 8x8 tiles
         const int mt = (NB - c1) / 8;
         int cnt = 0;
@@ -138,12 +167,16 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
             }
         }
         __syncthreads();
+        if (jb == 0) PCLK(5);
     }
-    for (int t = tid; t < nb * nb; t += 256) {
-        int r = t / nb, cidx = t % nb;
-        if (cidx <= r) A[(int64_t)r * lda + cidx] = s[r * PLD + cidx];
+    PCLK(6);
+#pragma unroll 8
+    for (int t = tid; t < NB * NB; t += 256) {
+        int r = t >> 7, cidx = t & (NB - 1);
+        if (r < nb && cidx <= r) A[(int64_t)r * lda + cidx] = s[r * PLD + cidx];
     }
     __syncthreads();
+    PCLK(7);
 
     // ------------------------------------------------------------------ phase 2: inv(L) in place
     // step A: M_kj = L_kj inv(D_j); each warp owns whole 8-row strips, so the update is safe in place
@@ -177,6 +210,7 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
         s[(SB * jb + r) * PLD + SB * jb + cidx] = Dv[jb * SB * DLD + r * DLD + cidx];
     }
     __syncthreads();
+    PCLK(8);
     // step B
     {
         const int tr = warp >> 1, tc0 = (warp & 1) * 2;
@@ -200,10 +234,12 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
                 __syncthreads();
             }
     }
+    PCLK(9);
     for (int t = tid; t < NB * NB; t += 256) {
         int r = t >> 7, cidx = t & (NB - 1);
         Dinv[t] = (r < nb && cidx <= r && cidx < nb) ? s[r * PLD + cidx] : 0.0;
     }
+    PCLK(10);
 }
 
 __global__ void logdet_kernel(int n, const double* __restrict__ L, int64_t ldl, double* __restrict__ out) {
@@ -271,9 +307,22 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
         T = (double*)dense_tmp(c, sizeof(double) * (size_t)n * NB);
         if (!T) return sfem_fail(c, SFEM_ERR_CUDA, "potrf: temporary allocation failed");
     }
-    for (int J0 = 0; J0 < n; J0 += NB2) {
+    // Look-ahead: the trailing update of column block J is split into (a) the columns of block J+1, done on the main
+    // stream right away, and (b) everything to the right of them, done on an auxiliary stream WHILE the main stream
+    // factorises block J+1 (a chain of small, latency-bound kernels).  (b) of successive blocks accumulate into the
+    // same entries, so they stay ordered on the auxiliary stream; the main stream waits for (b)(J-1) before (a)(J).
+    const bool lookahead = n > 2 * NB2;
+    if (lookahead && !c->aux_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
+    }
+    cudaStream_t main_stream = c->stream;
+    bool aux_busy = false;
+    int rc = SFEM_OK;
+    for (int J0 = 0; J0 < n && rc == SFEM_OK; J0 += NB2) {
         const int Jend = imin(J0 + NB2, n);           // one past the last column of this column block
-        for (int j0 = J0; j0 < Jend; j0 += NB) {
+        for (int j0 = J0; j0 < Jend && rc == SFEM_OK; j0 += NB) {
             int nb = imin(NB, n - j0);
             double* Ajj = A + (int64_t)j0 * lda + j0;
             double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
@@ -287,26 +336,49 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
             double* A21 = A + (int64_t)(j0 + nb) * lda + j0;
             double* A22 = A + (int64_t)(j0 + nb) * lda + (j0 + nb);
             c->dgemm_tag = TAG_CHOL_TRSM;
-            int rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);   // T = A21 inv(L_jj)^T
+            rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);   // T = A21 inv(L_jj)^T
             c->dgemm_tag = TAG_CHOL_SYRK;
             int ncols = Jend - (j0 + nb);              // columns of this column block still to be updated
             if (rc == SFEM_OK && ncols > 0)
                 rc = dgemm(c, OP_N, OP_T, m, ncols, nb, -1.0, T, NB, T, NB, 1.0, A22, lda, 1);   // lower tiles
             c->dgemm_tag = TAG_DGEMM;
-            if (rc) return rc;
+            if (rc) break;
             CUDA_TRY(c, cudaMemcpy2DAsync(A21, sizeof(double) * lda, T, sizeof(double) * NB, sizeof(double) * nb, m,
                                           cudaMemcpyDeviceToDevice, c->stream));
         }
+        if (rc) break;
         int m2 = n - Jend;
-        if (m2 > 0) {
-            const double* L2 = A + (int64_t)Jend * lda + J0;     // finished rows below the column block, its columns
-            c->dgemm_tag = TAG_CHOL_SYRK;
-            int rc = dgemm(c, OP_N, OP_T, m2, m2, Jend - J0, -1.0, L2, lda, L2, lda, 1.0, A + (int64_t)Jend * lda + Jend, lda, 1);
-            c->dgemm_tag = TAG_DGEMM;
-            if (rc) return rc;
+        if (m2 <= 0) continue;
+        const int kb = Jend - J0;
+        const double* L2 = A + (int64_t)Jend * lda + J0;     // finished rows below the column block, its columns
+        double* C22 = A + (int64_t)Jend * lda + Jend;
+        const int na = imin(NB2, m2);                        // (a): the next column block
+        c->dgemm_tag = TAG_CHOL_SYRK;
+        if (lookahead) {
+            CUDA_TRY(c, cudaEventRecord(c->ev_main, main_stream));          // block J is final
+            if (aux_busy) CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));   // (b)(J-1) done before (a)(J)
         }
+        rc = dgemm(c, OP_N, OP_T, m2, na, kb, -1.0, L2, lda, L2, lda, 1.0, C22, lda, 1);          // (a), lower tiles
+        if (rc == SFEM_OK && m2 > na) {
+            const double* L3 = L2 + (int64_t)na * lda;       // rows below the next column block
+            double* C33 = C22 + (int64_t)na * lda + na;
+            if (lookahead) {
+                CUDA_TRY(c, cudaStreamWaitEvent(c->aux_stream, c->ev_main, 0));
+                c->stream = c->aux_stream;
+            }
+            rc = dgemm(c, OP_N, OP_T, m2 - na, m2 - na, kb, -1.0, L3, lda, L3, lda, 1.0, C33, lda, 1);   // (b)
+            if (lookahead) {
+                cudaEventRecord(c->ev_aux, c->aux_stream);
+                c->stream = main_stream;
+                aux_busy = true;
+            }
+        }
+        c->dgemm_tag = TAG_DGEMM;
     }
-    return SFEM_OK;
+    c->stream = main_stream;
+    c->dgemm_tag = TAG_DGEMM;
+    if (aux_busy) CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
+    return rc;
 }
 
 // B (n x k, ldb) <- inv(L L^T) B.  ncols_tri > 0 limits the forward pass to a lower-trapezoidal RHS (potri).
@@ -408,3 +480,8 @@ int logdet_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, double* out_d
 }
 
 size_t potrf_dinv_doubles(int n) { return (size_t)((n + NB - 1) / NB) * NB * NB; }
+
+// diagnostic (not part of the public header): cycle stamps of the phases of the last panel kernel
+extern "C" int sfem_debug_panel_clocks(long long* out16_host) {
+    return cudaMemcpyFromSymbol(out16_host, g_panel_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}

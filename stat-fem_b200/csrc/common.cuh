@@ -71,6 +71,8 @@ struct sfem_ctx {
     void* scratch = nullptr; size_t scratch_bytes = 0;
     void* pinned = nullptr;          // small pinned host buffer for scalar read-backs
     void* dense_tmp = nullptr; size_t dense_tmp_bytes = 0;   // panel / trtri temporaries of chol.cu (owned, grows)
+    cudaStream_t aux_stream = nullptr;                        // look-ahead stream of the blocked Cholesky (owned, lazy)
+    cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
 };
 
 int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);
