@@ -330,7 +330,6 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-size_t mg_workspace_bytes(sfem_ctx* c, int k);
 size_t mg_tiles_workspace_bytes(sfem_ctx* c, int k);
 const int* mg_tiles_fine_perm(sfem_ctx* c);
 int mg_apply_tiles(sfem_ctx* c, int k, const double* R, double* Z, double* T0, double* T1, void* work, double* dot_partials, int* nparts);
@@ -486,8 +485,6 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     double* relres_dev = sc + 6 * k;
     s.active = (int*)w; s.n_active = s.active + k;
     w += align256(sizeof(int) * ((size_t)k + 8));
-    void* mgwork = w;
-
     bool v2 = can_vec2(k, k, ldx, R, X) && can_vec2(k, ldb, ldb, B, B);
     dim3 grid(g.nblk, v2 ? (k + 63) / 64 : (k + 31) / 32);
     int sb = (k + 127) / 128;
@@ -515,13 +512,6 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
     LAUNCH_VJ(jac ? 4 : 3, cg_init_kernel, n, k, B, ldb, X, ldx, R, P, c->A_dinv, part0, part1, g.rows_per_block);
     cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, jac ? part1 : nullptr, s, rtol, atol);
     KCHECK(c);
-    if (!jac) {
-        int rc = mg_apply(c, k, R, k, Z, k, Q, mgwork);
-        if (rc) return rc;
-        LAUNCH_V(3, cg_pz_kernel, n, k, R, Z, P, nullptr, part1, g.rows_per_block);
-        cg_rho_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part1, s);
-        KCHECK(c);
-    }
     CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     int it = 0;
@@ -532,11 +522,6 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
         cg_alpha_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s);
         KCHECK(c);
         LAUNCH_VJ(6, cg_update_kernel, n, k, s.alpha, P, Q, X, ldx, R, c->A_dinv, part1, part2, g.rows_per_block);
-        if (!jac) {
-            rc = mg_apply(c, k, R, k, Z, k, Q, mgwork);
-            if (rc) return rc;
-            LAUNCH_V(2, cg_pz_kernel, n, k, R, Z, (double*)nullptr, nullptr, part2, g.rows_per_block);
-        }
         CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
         cg_beta_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part1, part2, s);
         KCHECK(c);

@@ -255,13 +255,6 @@ __global__ void logdet_kernel(int n, const double* __restrict__ L, int64_t ldl, 
     if (threadIdx.x == 0) *out = 2.0 * sh[0];
 }
 
-__global__ void set_identity_kernel(int n, double* __restrict__ W, int64_t ld) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)n * n) return;
-    int i = (int)(t / n), j = (int)(t % n);
-    W[(int64_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
-}
-
 __global__ void mirror_lower_kernel(int n, double* __restrict__ A, int64_t ld) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n * n) return;

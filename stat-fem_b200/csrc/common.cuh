@@ -160,5 +160,4 @@ int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double
                   const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int batch,
                   int64_t strideA, int64_t strideB, int64_t strideC);
 // mg.cu
-int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_t ldz, double* tmp0, void* work);
 void mg_free(sfem_ctx* c);

@@ -64,13 +64,6 @@ __global__ void axpby_kernel(int n, double a, const double* __restrict__ x, doub
     if (i < n) z[i] = a * x[i] + (y ? b * y[i] : 0.0);
 }
 
-// C = A + s * B  (n x n matrices, ld n)
-__global__ void mat_axpy_kernel(int64_t tot, const double* __restrict__ A, double s, const double* __restrict__ B,
-                                double* __restrict__ C) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < tot) C[i] = A[i] + s * B[i];
-}
-
 // y = M x for a row-major n x n matrix: one warp per row, fixed-order shuffle reduction
 __global__ void __launch_bounds__(256) gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ x,
                                                   double* __restrict__ y) {

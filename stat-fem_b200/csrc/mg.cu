@@ -1,5 +1,6 @@
-// K4: lattice multigrid V-cycle preconditioner for the stiffness matrix, built on the GPU from (CSR A, DOF
-// coordinates, Dirichlet mask).
+// K4: lattice multigrid hierarchy for the stiffness matrix, built on the GPU from (CSR A, DOF coordinates, Dirichlet
+// mask).  This file builds the levels in the caller's numbering; mg_tiles.cu renumbers them, converts every operator
+// to the staged-tile format and runs the V-cycle.
 //
 // Hierarchy:  level 0 = the FEM matrix in CSR.  Level 1 = a regular lattice (2^p+1 nodes per direction, about half
 // the fine resolution) laid over the bounding box; fine DOFs interpolate multilinearly from the 2^d corners of the
@@ -15,11 +16,6 @@
 #include <cmath>
 
 int build_cell_list(sfem_ctx* c, const int* cell_of, int64_t n, int ncell, int** cell_start_out, int** cell_nodes_out);
-int csr_jacobi(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
-               const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
-               const double* dinv, double omega);
-int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
-                 const double* X, int64_t ldx, double* R, int64_t ldr, const double* B, int64_t ldb);
 
 namespace {
 
@@ -274,224 +270,6 @@ __global__ void dense_inverse_kernel(int n, double* __restrict__ A) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------- cycle kernels
-// x = omega * dinv .* b   (first smoothing sweep from a zero guess); constrained/identity rows give x = omega*b: the
-// coarse right-hand sides are zero there.  Generic over levels.
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) jacobi0_kernel(int64_t n, int k, const double* __restrict__ B, int64_t ldb,
-                                                            double* __restrict__ X, int64_t ldx,
-                                                            const double* __restrict__ dinv, double omega,
-                                                            int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> L(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
-    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
-        double b0, b1;
-        ld_cols<VEC>(B + row * ldb, L, b0, b1);
-        double w = omega * dinv[row];
-        st_cols<VEC>(X + row * ldx, L, w * b0, w * b1);
-    }
-}
-
-enum { LM_JACOBI = 0, LM_RESID = 1 };
-template <int VEC, int MODE>
-__global__ void __launch_bounds__(RB_THREADS) lat_block_kernel(Lat L, int d, const double* __restrict__ stencil, int k,
-                                                              const double* __restrict__ X, double* __restrict__ Y,
-                                                              const double* __restrict__ B,
-                                                              const double* __restrict__ dinv, double omega,
-                                                              int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < L.n ? r0 + rows_per_block : L.n;
-    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
-        const double* srow = stencil + row * L.S;
-        double a0 = 0.0, a1 = 0.0;
-        for (int s = 0; s < L.S; ++s) {
-            double a = srow[s];
-            if (a == 0.0) continue;
-            int o0, o1, o2;
-            slot_decode(d, s, o0, o1, o2);
-            int64_t nb = row + o0 + (int64_t)L.m0 * (o1 + (int64_t)L.m1 * o2);
-            double x0, x1;
-            ld_cols<VEC>(X + nb * k, C, x0, x1);
-            a0 += a * x0; a1 += a * x1;
-        }
-        double b0, b1;
-        ld_cols<VEC>(B + row * k, C, b0, b1);
-        if (MODE == LM_JACOBI) {
-            double x0, x1;
-            ld_cols<VEC>(X + row * k, C, x0, x1);
-            double w = omega * dinv[row];
-            a0 = x0 + w * (b0 - a0); a1 = x1 + w * (b1 - a1);
-        } else {
-            a0 = b0 - a0; a1 = b1 - a1;
-        }
-        st_cols<VEC>(Y + row * k, C, a0, a1);
-    }
-}
-
-// b1[I] = sum_i w_iI r[i]   (fine CSR level -> level-1 lattice); warp per lattice node
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) fine_restrict_kernel(Lat L, int d, int k, const double* __restrict__ R, int64_t ldr,
-                                                                  double* __restrict__ Bc, const int* __restrict__ cell_start,
-                                                                  const int* __restrict__ cell_nodes,
-                                                                  const double* __restrict__ frac,
-                                                                  const unsigned char* __restrict__ bc,
-                                                                  const unsigned char* __restrict__ constrained,
-                                                                  int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < L.n ? r0 + rows_per_block : L.n;
-    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1, mc2 = d > 2 ? L.m2 - 1 : 1;
-    for (int64_t node = r0 + warp; node < r1; node += RB_WARPS) {
-        double a0 = 0.0, a1 = 0.0;
-        if (!constrained[node]) {
-            int i0, i1, i2;
-            lat_decode(L, (int)node, i0, i1, i2);
-            for (int beta = 0; beta < (1 << d); ++beta) {
-                int c0 = i0 - (beta & 1), c1 = i1 - ((beta >> 1) & 1), c2 = i2 - ((beta >> 2) & 1);
-                if (c0 < 0 || c0 >= mc0 || c1 < 0 || c1 >= mc1 || c2 < 0 || c2 >= mc2) continue;
-                int cell = c0 + mc0 * (c1 + mc1 * c2);
-                for (int q = cell_start[cell]; q < cell_start[cell + 1]; ++q) {
-                    int i = cell_nodes[q];
-                    if (bc[i]) continue;
-                    double w = corner_weight(d, frac + (int64_t)i * d, beta);
-                    if (w == 0.0) continue;
-                    double x0, x1;
-                    ld_cols<VEC>(R + (int64_t)i * ldr, C, x0, x1);
-                    a0 += w * x0; a1 += w * x1;
-                }
-            }
-        }
-        st_cols<VEC>(Bc + node * k, C, a0, a1);
-    }
-}
-
-// x[i] += sum_corners w x1[I]   (level-1 lattice -> fine); warp per fine node
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) fine_prolong_kernel(int64_t n, Lat L, int d, int k, double* __restrict__ X, int64_t ldx,
-                                                                 const double* __restrict__ Xc, const int* __restrict__ cidx,
-                                                                 const double* __restrict__ frac,
-                                                                 const unsigned char* __restrict__ bc, int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
-    int mc0 = L.m0 - 1, mc1 = d > 1 ? L.m1 - 1 : 1;
-    for (int64_t i = r0 + warp; i < r1; i += RB_WARPS) {
-        if (bc[i]) continue;
-        int cj = cidx[i];
-        int j0 = cj % mc0, tq = cj / mc0;
-        int j1 = tq % mc1, j2 = tq / mc1;
-        double a0, a1;
-        ld_cols<VEC>(X + i * ldx, C, a0, a1);
-        for (int g = 0; g < (1 << d); ++g) {
-            double w = corner_weight(d, frac + i * d, g);
-            if (w == 0.0) continue;
-            int64_t I = lat_index(L, j0 + (g & 1), j1 + ((g >> 1) & 1), j2 + ((g >> 2) & 1));
-            double x0, x1;
-            ld_cols<VEC>(Xc + I * k, C, x0, x1);
-            a0 += w * x0; a1 += w * x1;
-        }
-        st_cols<VEC>(X + i * ldx, C, a0, a1);
-    }
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) lat_restrict_kernel(LatPair P, int k, const double* __restrict__ R,
-                                                                 double* __restrict__ Bc, const unsigned char* __restrict__ cf,
-                                                                 const unsigned char* __restrict__ cc, int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < P.C.n ? r0 + rows_per_block : P.C.n;
-    int d = P.d;
-    int q0 = P.co[0] ? 1 : 0, q1 = (d > 1 && P.co[1]) ? 1 : 0, q2 = (d > 2 && P.co[2]) ? 1 : 0;
-    int s0 = P.co[0] ? 2 : 1, s1 = P.co[1] ? 2 : 1, s2 = P.co[2] ? 2 : 1;
-    for (int64_t node = r0 + warp; node < r1; node += RB_WARPS) {
-        double a0 = 0.0, a1 = 0.0;
-        if (!cc[node]) {
-            int I0, I1, I2;
-            lat_decode(P.C, (int)node, I0, I1, I2);
-            for (int e2 = -q2; e2 <= q2; ++e2)
-                for (int e1 = -q1; e1 <= q1; ++e1)
-                    for (int e0 = -q0; e0 <= q0; ++e0) {
-                        int i0 = s0 * I0 + e0, i1 = s1 * I1 + e1, i2 = s2 * I2 + e2;
-                        if (i0 < 0 || i0 >= P.F.m0 || i1 < 0 || i1 >= P.F.m1 || i2 < 0 || i2 >= P.F.m2) continue;
-                        int64_t fi = lat_index(P.F, i0, i1, i2);
-                        if (cf[fi]) continue;
-                        double w = w1d(P.co[0], e0) * w1d(P.co[1], e1) * w1d(P.co[2], e2);
-                        double x0, x1;
-                        ld_cols<VEC>(R + fi * k, C, x0, x1);
-                        a0 += w * x0; a1 += w * x1;
-                    }
-        }
-        st_cols<VEC>(Bc + node * k, C, a0, a1);
-    }
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) lat_prolong_kernel(LatPair P, int k, double* __restrict__ X,
-                                                                const double* __restrict__ Xc,
-                                                                const unsigned char* __restrict__ cf, int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < P.F.n ? r0 + rows_per_block : P.F.n;
-    for (int64_t fi = r0 + warp; fi < r1; fi += RB_WARPS) {
-        if (cf[fi]) continue;
-        int i[3];
-        lat_decode(P.F, (int)fi, i[0], i[1], i[2]);
-        int base[3], cnt[3];
-        double w[3];
-        for (int q = 0; q < 3; ++q) {
-            if (q < P.d && P.co[q]) {
-                if (i[q] & 1) { base[q] = (i[q] - 1) >> 1; cnt[q] = 2; w[q] = 0.5; }
-                else { base[q] = i[q] >> 1; cnt[q] = 1; w[q] = 1.0; }
-            } else { base[q] = i[q]; cnt[q] = 1; w[q] = 1.0; }
-        }
-        double a0, a1;
-        ld_cols<VEC>(X + fi * k, C, a0, a1);
-        for (int c2 = 0; c2 < cnt[2]; ++c2)
-            for (int c1 = 0; c1 < cnt[1]; ++c1)
-                for (int c0 = 0; c0 < cnt[0]; ++c0) {
-                    int64_t I = lat_index(P.C, base[0] + c0, base[1] + c1, base[2] + c2);
-                    double x0, x1;
-                    ld_cols<VEC>(Xc + I * k, C, x0, x1);
-                    double ww = w[0] * w[1] * w[2];
-                    a0 += ww * x0; a1 += ww * x1;
-                }
-        st_cols<VEC>(X + fi * k, C, a0, a1);
-    }
-}
-
-// x = Ainv b on the coarsest lattice (dense)
-template <int VEC>
-__global__ void __launch_bounds__(RB_THREADS) dense_apply_kernel(int n, int k, const double* __restrict__ Ainv,
-                                                                const double* __restrict__ B, double* __restrict__ X,
-                                                                int64_t rows_per_block) {
-    const int warp = threadIdx.x >> 5;
-    LaneCols<VEC> C(k);
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
-    for (int64_t row = r0 + warp; row < r1; row += RB_WARPS) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int j = 0; j < n; ++j) {
-            double a = Ainv[row * n + j];
-            if (a == 0.0) continue;
-            double x0, x1;
-            ld_cols<VEC>(B + (int64_t)j * k, C, x0, x1);
-            a0 += a * x0; a1 += a * x1;
-        }
-        st_cols<VEC>(X + row * k, C, a0, a1);
-    }
-}
-
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 }  // namespace
 
 void mg_tiles_free(MGLevel* L);
@@ -632,114 +410,5 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
     return mg_build_tiles(c);
 }
 
-// workspace: for every lattice level: bufA, bufB, b  (each n_l x k)
-size_t mg_workspace_bytes(sfem_ctx* c, int k) {
-    size_t bytes = 0;
-    for (size_t l = 1; l < c->mg.size(); ++l) bytes += 3 * align256(sizeof(double) * (size_t)c->mg[l]->n * k);
-    return bytes + 256;
-}
-
 int mg_num_levels(sfem_ctx* c) { return (int)c->mg.size(); }
 int64_t mg_level_size(sfem_ctx* c, int l) { return (l >= 0 && l < (int)c->mg.size()) ? c->mg[l]->n : -1; }
-
-#define MG_LAUNCH(tag, bytes, nrows, kern, ...)                                                      \
-    do {                                                                                             \
-        ProfScope _ps(c, tag, bytes, 0.0);                                                           \
-        RowGrid _g = row_grid(nrows);                                                                \
-        if (v2) kern<2> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
-        else kern<1> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
-        KCHECK(c);                                                                                   \
-    } while (0)
-#define MG_LAUNCH2(tag, bytes, nrows, kern, MODE, ...)                                               \
-    do {                                                                                             \
-        ProfScope _ps(c, tag, bytes, 0.0);                                                           \
-        RowGrid _g = row_grid(nrows);                                                                \
-        if (v2) kern<2, MODE> <<<dim3(_g.nblk, (k + 63) / 64), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block); \
-        else kern<1, MODE> <<<dim3(_g.nblk, (k + 31) / 32), RB_THREADS, 0, c->stream>>>(__VA_ARGS__, _g.rows_per_block);    \
-        KCHECK(c);                                                                                   \
-    } while (0)
-
-// Z = M^-1 R  (one V-cycle).  R: [n x k] ld ldr.  Z: ld ldz.  tmp0: [n x k] ld k (scratch on the fine level).
-int mg_apply(sfem_ctx* c, int k, const double* R, int64_t ldr, double* Z, int64_t ldz, double* tmp0, void* work) {
-    int nl = (int)c->mg.size();
-    if (nl < 2) return sfem_fail(c, SFEM_ERR_STATE, "mg_apply: hierarchy not built");
-    const int nu = c->mg_nu_pre;
-    const double om = 1.0;   // the damping factor is folded into the per-level dinv arrays (exact on identity rows)
-    bool v2 = (k % 2 == 0) && (ldr % 2 == 0) && (ldz % 2 == 0) &&
-              ((reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(tmp0)) % 16 == 0);
-    // carve lattice-level buffers
-    std::vector<double*> bufA(nl), bufB(nl), rhs(nl);
-    unsigned char* w = (unsigned char*)work;
-    for (int l = 1; l < nl; ++l) {
-        size_t sz = align256(sizeof(double) * (size_t)c->mg[l]->n * k);
-        bufA[l] = (double*)w; w += sz;
-        bufB[l] = (double*)w; w += sz;
-        rhs[l] = (double*)w; w += sz;
-    }
-    std::vector<double*> xcur(nl);
-    std::vector<int64_t> xld(nl);
-    MGLevel* L0 = c->mg[0];
-    int64_t n = L0->n;
-    // ---------------- level 0, downward.  2*nu - 1 buffer swaps in total: start in tmp0, finish in Z.
-    double* cur = tmp0; int64_t ldc = k;
-    double* oth = Z; int64_t ldo = ldz;
-    auto swap0 = [&]() { std::swap(cur, oth); std::swap(ldc, ldo); };
-    MG_LAUNCH(TAG_MG_XFER, 16.0 * (double)n * k, n, jacobi0_kernel, n, k, R, ldr, cur, ldc, L0->dinv, om);
-    for (int s = 1; s < nu; ++s) {
-        int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
-        if (rc) return rc;
-        swap0();
-    }
-    {
-        int rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr);
-        if (rc) return rc;
-    }
-    Lat lat1 = make_lat(c->mg[1]->d, c->mg[1]->m);
-    MG_LAUNCH(TAG_MG_XFER, 8.0 * (double)(n + lat1.n) * k, lat1.n, fine_restrict_kernel, lat1, L0->d, k, oth, ldo, rhs[1], L0->cell_start, L0->cell_nodes, L0->frac,
-              L0->constrained, c->mg[1]->constrained);
-    // ---------------- lattice levels, downward
-    for (int l = 1; l < nl; ++l) {
-        MGLevel* L = c->mg[l];
-        Lat lat = make_lat(L->d, L->m);
-        if (l == nl - 1 && L->dense_inv) {
-            MG_LAUNCH(TAG_MG_LATTICE, 16.0 * (double)lat.n * k, lat.n, dense_apply_kernel, (int)lat.n, k, L->dense_inv, rhs[l], bufA[l]);
-            xcur[l] = bufA[l];
-            break;
-        }
-        double* a = bufA[l];
-        double* b = bufB[l];
-        MG_LAUNCH(TAG_MG_LATTICE, 16.0 * (double)lat.n * k, lat.n, jacobi0_kernel, lat.n, k, rhs[l], (int64_t)k, a, (int64_t)k, L->dinv, om);
-        int sweeps = (l == nl - 1) ? 8 * nu : nu;    // no dense inverse available: smooth harder on the last level
-        for (int s = 1; s < sweeps; ++s) {
-            MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
-            std::swap(a, b);
-        }
-        xcur[l] = a;
-        if (l == nl - 1) break;
-        MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_RESID, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
-        LatPair P = make_pair(L, c->mg[l + 1]);
-        MG_LAUNCH(TAG_MG_LATTICE, 8.0 * (double)(P.F.n + P.C.n) * k, P.C.n, lat_restrict_kernel, P, k, b, rhs[l + 1], L->constrained, c->mg[l + 1]->constrained);
-    }
-    // ---------------- upward
-    for (int l = nl - 2; l >= 1; --l) {
-        MGLevel* L = c->mg[l];
-        Lat lat = make_lat(L->d, L->m);
-        LatPair P = make_pair(L, c->mg[l + 1]);
-        double* a = xcur[l];
-        double* b = (a == bufA[l]) ? bufB[l] : bufA[l];
-        MG_LAUNCH(TAG_MG_LATTICE, 8.0 * (double)(2 * P.F.n + P.C.n) * k, lat.n, lat_prolong_kernel, P, k, a, xcur[l + 1], L->constrained);
-        for (int s = 0; s < nu; ++s) {
-            MG_LAUNCH2(TAG_MG_LATTICE, (24.0 * k + 8.0 * lat.S) * (double)lat.n, lat.n, lat_block_kernel, LM_JACOBI, lat, L->d, L->stencil, k, a, b, rhs[l], L->dinv, om);
-            std::swap(a, b);
-        }
-        xcur[l] = a;
-    }
-    MG_LAUNCH(TAG_MG_XFER, 8.0 * (double)(2 * n + lat1.n) * k, n, fine_prolong_kernel, n, lat1, L0->d, k, cur, ldc, xcur[1], L0->cidx, L0->frac, L0->constrained);
-    for (int s = 0; s < nu; ++s) {
-        int rc = csr_jacobi(c, n, c->A_ptr, c->A_idx, c->A_val, k, cur, ldc, oth, ldo, R, ldr, L0->dinv, om);
-        if (rc) return rc;
-        swap0();
-    }
-    if (cur != Z) return sfem_fail(c, SFEM_ERR_STATE, "mg_apply: internal buffer parity error");
-    return SFEM_OK;
-}

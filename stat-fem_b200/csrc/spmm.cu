@@ -2,8 +2,7 @@
 //
 //   MODE_MULT     Y = S X                                   (G Z, P d, P^T v, final residual check)
 //   MODE_MULT_DOT Y = S X,  partials[blk][c] = sum_i X[i][c] Y[i][c]      (q = A p and p^T A p of CG)
-//   MODE_JACOBI   Y = X + omega * dinv .* (B - S X)         (multigrid smoother on the fine level)
-//   MODE_RESID    Y = B - S X                               (multigrid residual on the fine level)
+//   MODE_RESID    Y = B - S X                               (true-residual check at the end of a block solve)
 //
 // Mapping: one warp owns a row at a time, lanes run across the RHS columns (double2 per lane -> 512-byte fully
 // coalesced requests per gathered row); (col, val) of the sparse row are warp-uniform broadcast loads.  A
@@ -12,10 +11,11 @@
 // are needed and the per-block partials are summed in a fixed order by a tiny follow-up kernel (deterministic).
 //
 // Replaces PETSc MatMult at ForcingCovariance.py:242 (G x), InterpolationMatrix.py:219/255 (P d, P^T v) and the
-// operator applications inside the KSP solves of solving_utils.py:51-53.
+// operator applications inside the Jacobi-preconditioned KSP solves (pc_type jacobi) of solving_utils.py:51-53; the
+// multigrid-preconditioned path uses the staged-tile kernels of tileop.cu instead.
 #include "rowops.cuh"
 
-enum { MODE_MULT = 0, MODE_MULT_DOT = 1, MODE_JACOBI = 2, MODE_RESID = 3 };
+enum { MODE_MULT = 0, MODE_MULT_DOT = 1, MODE_RESID = 3 };
 
 namespace {
 
@@ -41,12 +41,6 @@ __global__ void __launch_bounds__(RB_THREADS) csr_block_kernel(int64_t n, const 
             double x0, x1;
             ld_cols<VEC>(X + row * ldx, L, x0, x1);
             d0 += x0 * a0; d1 += x1 * a1;
-        } else if (MODE == MODE_JACOBI) {
-            double x0, x1, b0, b1;
-            ld_cols<VEC>(X + row * ldx, L, x0, x1);
-            ld_cols<VEC>(B + row * ldb, L, b0, b1);
-            double w = omega * dinv[row];
-            a0 = x0 + w * (b0 - a0); a1 = x1 + w * (b1 - a1);
         } else if (MODE == MODE_RESID) {
             double b0, b1;
             ld_cols<VEC>(B + row * ldb, L, b0, b1);
@@ -71,8 +65,8 @@ int launch_mode(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr
                 const double* dinv, double omega, double* partials) {
     RowGrid g = row_grid(n);
     // algorithmic traffic: the matrix once, each vector block once
-    double vecs = (MODE == MODE_JACOBI || MODE == MODE_RESID) ? 24.0 : 16.0;
-    ProfScope ps(c, tag, vecs * (double)n * k + 12.0 * (double)nnz + 8.0 * (double)(n + 1) + (MODE == MODE_JACOBI ? 8.0 * n : 0.0),
+    double vecs = (MODE == MODE_RESID) ? 24.0 : 16.0;
+    ProfScope ps(c, tag, vecs * (double)n * k + 12.0 * (double)nnz + 8.0 * (double)(n + 1),
                  2.0 * (double)nnz * k);
     bool v2 = can_vec2(k, ldx, ldy, X, Y) && (B == nullptr || can_vec2(k, ldb, ldb, B, B));
     if (v2) {
@@ -97,13 +91,6 @@ int spmm_csr(sfem_ctx* c, int tag, int64_t nnz, int64_t n, const int64_t* ptr, c
     if (dot_partials)
         return launch_mode<MODE_MULT_DOT>(c, tag, nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, dot_partials);
     return launch_mode<MODE_MULT>(c, tag, nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, nullptr, 0, nullptr, 0.0, nullptr);
-}
-
-// the two fine-level multigrid operators always act on the stiffness matrix held by the context
-int csr_jacobi(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
-               const double* X, int64_t ldx, double* Y, int64_t ldy, const double* B, int64_t ldb,
-               const double* dinv, double omega) {
-    return launch_mode<MODE_JACOBI>(c, TAG_CSR_JACOBI, c->A_nnz, n, ptr, idx, val, k, X, ldx, Y, ldy, B, ldb, dinv, omega, nullptr);
 }
 
 int csr_residual(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, int k,
