@@ -77,7 +77,7 @@ class ForcingCovariance(object):
         n, d = coords.shape
         int_basis = self._integrate_basis_functions()
         R = self._search_radius(int_basis)
-        lo, hi = coords.min(axis=0), coords.max(axis=0)
+        lo, hi = self.function_space.bounding_box()
         if R < 0.:
             cell_edge = float(max((hi - lo).max(), 1.) * 1.e-3)      # diagonal only: any small cell will do
             cell_edge = max(cell_edge, float((hi - lo).max()) / 2048.)

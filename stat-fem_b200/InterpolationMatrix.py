@@ -49,12 +49,10 @@ class InterpolationMatrix(object):
         mesh = self.function_space.mesh()
         cells, weights = mesh.locate_cells(self.coords)
         nodes = self.function_space.cell_node_list
-        rows, cols, vals = [], [], []
-        for i in range(self.n_data):
-            if cells[i] >= 0:
-                rows.extend(nodes[cells[i]])
-                cols.extend([i] * nodes.shape[1])
-                vals.extend(weights[i])
+        inside = np.nonzero(cells >= 0)[0]
+        rows = nodes[cells[inside]].ravel()
+        cols = np.repeat(inside, nodes.shape[1])
+        vals = weights[inside].ravel()
         P = sp.csc_matrix((vals, (rows, cols)), shape=(self.n_mesh, self.n_data))
         P.sort_indices()
         self.interp = P

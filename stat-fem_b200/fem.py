@@ -115,20 +115,29 @@ class Mesh(object):
         binid = np.zeros(pts.shape[0], dtype=np.int64)
         for k in range(d):
             binid = binid * nb + ib[:, k]
-        cells_out = np.full(pts.shape[0], -1, dtype=np.int64)
-        w_out = np.zeros((pts.shape[0], d + 1))
-        for p in range(pts.shape[0]):
-            cand = L["bin_cells"][L["bin_ptr"][binid[p]]:L["bin_ptr"][binid[p] + 1]]
-            if cand.size == 0:
-                continue
-            V = self.coords[self.cells[cand]]
+        npts = pts.shape[0]
+        cells_out = np.full(npts, -1, dtype=np.int64)
+        w_out = np.zeros((npts, d + 1))
+        best_min = np.full(npts, -np.inf)
+        start = L["bin_ptr"][binid]
+        count = L["bin_ptr"][binid + 1] - start
+        # k-th candidate cell of every point at once (vectorised over the points; bins hold a handful of cells)
+        for k in range(int(count.max()) if npts else 0):
+            sel = np.nonzero(count > k)[0]
+            cand = L["bin_cells"][start[sel] + k]
+            V = self.coords[self.cells[cand]]                                # (m, d+1, d)
             T = np.transpose(V[:, 1:, :] - V[:, :1, :], (0, 2, 1))
-            lam = np.linalg.solve(T, (pts[p][None, :] - V[:, 0, :])[:, :, None])[:, :, 0]
+            lam = np.linalg.solve(T, (pts[sel] - V[:, 0, :])[:, :, None])[:, :, 0]
             lam = np.concatenate([(1. - lam.sum(axis=1))[:, None], lam], axis=1)
-            best = int(np.argmax(lam.min(axis=1)))
-            if lam[best].min() >= -tol:
-                cells_out[p] = cand[best]
-                w_out[p] = lam[best]
+            lmin = lam.min(axis=1)
+            better = lmin > best_min[sel]                                    # first best candidate wins, as argmax did
+            idx = sel[better]
+            best_min[idx] = lmin[better]
+            cells_out[idx] = cand[better]
+            w_out[idx] = lam[better]
+        outside = best_min < -tol
+        cells_out[outside] = -1
+        w_out[outside] = 0.
         return cells_out, w_out
 
     def locate_cell(self, x, tol=1.e-12):
@@ -202,6 +211,13 @@ class P1Space(object):
     @property
     def coords(self):
         return self._mesh.coords
+
+    def bounding_box(self):
+        "(lo, hi) of the DOF coordinates, computed once (two passes over n x d doubles)"
+        if self.__dict__.get("_bbox") is None:
+            c = self._mesh.coords
+            self._bbox = (np.array([c[:, k].min() for k in range(c.shape[1])]), np.array([c[:, k].max() for k in range(c.shape[1])]))
+        return self._bbox[0].copy(), self._bbox[1].copy()
 
     def cell_volumes(self):
         V = self._mesh.coords[self._mesh.cells]

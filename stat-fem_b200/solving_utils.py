@@ -17,14 +17,14 @@ _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_si
                       "mg_max_coarse", "workspace_gb"}
 
 
-def _lattice_nodes(coords):
+def _lattice_nodes(coords, bbox=None):
     """level-1 lattice: 2^p cells per direction.  Preferred: a spacing of exactly TWICE the estimated mesh width,
     anchored at the lower corner of the bounding box and overhanging the upper corner (by at most 25 %): on lattice-like
     meshes every DOF then sits on a lattice node, edge midpoint or cell centre, the transfer weights are exactly 0, 1/2,
     1/4, 1, and all Galerkin coarse operators stay compact (3^d points) instead of filling their 5^d stencils.
     Otherwise the lattice is stretched over the box with a spacing of 1.5 to 3 mesh widths."""
     n, d = coords.shape
-    lo, hi = coords.min(axis=0), coords.max(axis=0)
+    lo, hi = bbox if bbox is not None else (coords.min(axis=0), coords.max(axis=0))
     ext = np.where(hi > lo, hi - lo, 1.)
     geo = float(np.prod(ext) ** (1. / d))
     per_side = float(n) ** (1. / d)
@@ -101,7 +101,7 @@ class SparseSolver(object):
         ctx, lib = self.ctx, _lib.lib()
         coords = np.ascontiguousarray(self.A.function_space.coords, dtype=np.float64)
         n, d = coords.shape
-        lo, hi, m1 = _lattice_nodes(coords)
+        lo, hi, m1 = _lattice_nodes(coords, self.A.function_space.bounding_box())
         mask = np.zeros(n, dtype=np.uint8)
         mask[self.bc_nodes] = 1
         self._d_coords = _lib.cached_upload(self.A.function_space, "coords", ctx, lambda: ctx.to_device(coords, np.float64))
