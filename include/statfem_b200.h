@@ -106,6 +106,27 @@ int sfem_gcov_fill(sfem_ctx* ctx, const int64_t* indptr, int32_t* indices_out, d
  * sfem_dgemm(T, N, n_obs, n_cols, n_dof, 1, W, ldw, Z, ldz, 0, Cu, ldcu)  (solving_utils.py:139-142, 164-169). */
 int sfem_dgemm(sfem_ctx* ctx, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
                const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+/* Symmetric split of the covariance assembly: with G = S + E (E: the entries of G whose transpose is not stored --
+ * ForcingCovariance.py:160-164 drops (j, i) but keeps (i, j) only next to the boundary), (G Z)^T Z = (S Z)^T Z + (E Z)^T Z
+ * where the first term is symmetric (sfem_dgemm_lower + sfem_mirror_lower: half the tiles) and the second sums over
+ * the few non-empty rows of E only.  sfem_csr_unsym_count / _fill extract E as a compact-row CSR (rows_out lists the
+ * non-empty rows); scratch arrays: row_cnt, row_flag n int64; eptr_full, rowpos n + 1 int64 (all device). */
+int sfem_csr_unsym_count(sfem_ctx* ctx, int64_t n, const int64_t* indptr, const int32_t* indices, int64_t* row_cnt,
+                         int64_t* row_flag, int64_t* eptr_full, int64_t* rowpos, int64_t* nrows_out_host,
+                         int64_t* nnz_out_host);
+int sfem_csr_unsym_fill(sfem_ctx* ctx, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals,
+                        const int64_t* eptr_full, const int64_t* rowpos, int32_t* rows_out, int64_t* eptr_out,
+                        int32_t* eidx_out, double* eval_out);
+/* Y[rows[r]] += alpha X[r]  and  X[r] = Y[rows[r]]  for row-major blocks of k columns */
+int sfem_rows_axpy(sfem_ctx* ctx, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx,
+                   double* Y, int64_t ldy);
+int sfem_rows_gather(sfem_ctx* ctx, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X,
+                     int64_t ldx);
+/* C (n x n) = alpha op(A) op(B) + beta C on the 128x128 tiles on and below the diagonal only; sfem_mirror_lower copies
+ * the strict lower triangle onto the upper one. */
+int sfem_dgemm_lower(sfem_ctx* ctx, int opA, int opB, int n, int64_t K, double alpha, const double* A, int64_t lda,
+                     const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+int sfem_mirror_lower(sfem_ctx* ctx, int n, double* A, int64_t lda);
 size_t sfem_potrf_dinv_doubles(int n);
 /* In-place lower Cholesky of the row-major n x n matrix A (only the lower triangle is read); dinv receives the
  * inverses of the 128x128 diagonal blocks.  info_out_host: 0 or the 1-based index of the first non-positive pivot. */

@@ -109,6 +109,32 @@ class ForcingCovariance(object):
         self.G = _lib.DeviceCSR(ctx, (n, n), d_indptr, d_indices, d_vals, on_device=True)
         self.is_assembled = True
 
+    def unsymmetric_part(self):
+        """(rows, E) with E the compact-row device CSR of the entries of G whose transpose is not stored, and ``rows``
+        the (device, int32) indices of its non-empty rows; cached.  G - E is exactly symmetric (see csrc/symsplit.cu)."""
+        if not self.is_assembled:
+            self.assemble()
+        if self.__dict__.get("_unsym") is None:
+            import torch
+            ctx, lib, G = self.G.ctx, _lib.lib(), self.G
+            n = self.nx
+            cnt, flag = ctx.empty((n,), torch.int64), ctx.empty((n,), torch.int64)
+            efull, rowpos = ctx.empty((n + 1,), torch.int64), ctx.empty((n + 1,), torch.int64)
+            nrows, nnz = C.c_int64(0), C.c_int64(0)
+            ctx.check(lib.sfem_csr_unsym_count(ctx.handle, n, _lib.ptr(G.indptr), _lib.ptr(G.indices), _lib.ptr(cnt), _lib.ptr(flag),
+                                               _lib.ptr(efull), _lib.ptr(rowpos), C.byref(nrows), C.byref(nnz)))
+            rows = ctx.empty((max(nrows.value, 1),), torch.int32)
+            eptr = ctx.zeros((nrows.value + 1,), torch.int64)
+            eidx = ctx.empty((max(nnz.value, 1),), torch.int32)
+            evals = ctx.empty((max(nnz.value, 1),), torch.float64)
+            if nrows.value:
+                ctx.check(lib.sfem_csr_unsym_fill(ctx.handle, n, _lib.ptr(G.indptr), _lib.ptr(G.indices), _lib.ptr(G.data),
+                                                  _lib.ptr(efull), _lib.ptr(rowpos), _lib.ptr(rows), _lib.ptr(eptr), _lib.ptr(eidx),
+                                                  _lib.ptr(evals)))
+            E = _lib.DeviceCSR(ctx, (nrows.value, n), eptr, eidx[:nnz.value], evals[:nnz.value], on_device=True)
+            self._unsym = (rows[:nrows.value], E)
+        return self._unsym
+
     def _redecide(self, ctx, d_indptr, d_indices, d_vals, d_border, coords, int_basis):
         """Splice host-decided rows into the CSR arrays (rare: a ratio landed within 1e-14 of the cutoff)."""
         n = self.nx
@@ -146,6 +172,7 @@ class ForcingCovariance(object):
         if not self.is_assembled:
             return
         self.G = None
+        self._unsym = None
         self.is_assembled = False
 
     def mult(self, x, y):

@@ -22,7 +22,8 @@ EXPORTS = [
     "sfem_gcov_count", "sfem_gcov_fill", "sfem_dgemm", "sfem_potrf_dinv_doubles", "sfem_potrf", "sfem_potrs",
     "sfem_potri", "sfem_logdet", "sfem_kernel_matrix", "sfem_dense_workspace_bytes", "sfem_logpost",
     "sfem_posterior_cov", "sfem_dense_solve", "sfem_cov_matrix", "sfem_axpby", "sfem_profile_enable", "sfem_profile_num_tags",
-    "sfem_profile_tag_name", "sfem_profile_read",
+    "sfem_profile_tag_name", "sfem_profile_read", "sfem_csr_unsym_count", "sfem_csr_unsym_fill", "sfem_rows_axpy",
+    "sfem_rows_gather", "sfem_dgemm_lower", "sfem_mirror_lower",
 ]
 
 
@@ -69,6 +70,12 @@ def load_library():
         "sfem_posterior_cov": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, vp, C.POINTER(f64), vp, vp, vp, sz]),
         "sfem_cov_matrix": (i32, [vp, i32, i32, i32, vp, vp, f64, f64, i32, vp]),
         "sfem_axpby": (i32, [vp, i64, f64, vp, f64, vp, vp]),
+        "sfem_csr_unsym_count": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
+        "sfem_csr_unsym_fill": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "sfem_rows_axpy": (i32, [vp, i64, vp, i32, f64, vp, i64, vp, i64]),
+        "sfem_rows_gather": (i32, [vp, i64, vp, i32, vp, i64, vp, i64]),
+        "sfem_dgemm_lower": (i32, [vp, i32, i32, i32, i64, f64, vp, i64, vp, i64, f64, vp, i64]),
+        "sfem_mirror_lower": (i32, [vp, i32, vp, i64]),
         "sfem_dense_solve": (i32, [vp, i32, i32, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, sz]),
     }
     for name, (res, args) in sig.items():

@@ -22,6 +22,13 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
                const double* hi, int64_t* indptr_out, int64_t* nnz_out, int64_t* max_row_nnz_out,
                int32_t* borderline_rows, int borderline_cap, int64_t* n_borderline_out);
 int gcov_fill(sfem_ctx* c, const int64_t* indptr, int32_t* indices_out, double* vals_out);
+int unsym_count(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, int64_t* row_cnt, int64_t* row_flag,
+                int64_t* eptr_full, int64_t* rowpos, int64_t* nrows_host, int64_t* nnz_host);
+int unsym_fill(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const int64_t* eptr_full,
+               const int64_t* rowpos, int32_t* rows_out, int64_t* eptr_out, int32_t* eidx_out, double* eval_out);
+int rows_axpy(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx, double* Y, int64_t ldy);
+int rows_gather(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X, int64_t ldx);
+int mirror_lower(sfem_ctx* c, int n, double* A, int64_t ld);
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev);
 int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, int k, double* B, int64_t ldb);
 int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv);
@@ -224,6 +231,36 @@ int sfem_cov_matrix(sfem_ctx* c, int m, int n, int dim, const double* X1, const 
     GUARD(c);
     return dense_cov_matrix(c, m, n, dim, X1, X2, sigma, l, which, M_out);
 }
+int sfem_csr_unsym_count(sfem_ctx* c, int64_t n, const int64_t* indptr, const int32_t* indices, int64_t* row_cnt, int64_t* row_flag,
+                         int64_t* eptr_full, int64_t* rowpos, int64_t* nrows_out_host, int64_t* nnz_out_host) {
+    GUARD(c);
+    return unsym_count(c, n, indptr, indices, row_cnt, row_flag, eptr_full, rowpos, nrows_out_host, nnz_out_host);
+}
+int sfem_csr_unsym_fill(sfem_ctx* c, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals,
+                        const int64_t* eptr_full, const int64_t* rowpos, int32_t* rows_out, int64_t* eptr_out, int32_t* eidx_out,
+                        double* eval_out) {
+    GUARD(c);
+    return unsym_fill(c, n, indptr, indices, vals, eptr_full, rowpos, rows_out, eptr_out, eidx_out, eval_out);
+}
+int sfem_rows_axpy(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx, double* Y, int64_t ldy) {
+    GUARD(c);
+    return rows_axpy(c, nrows, rows, k, alpha, X, ldx, Y, ldy);
+}
+int sfem_rows_gather(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X, int64_t ldx) {
+    GUARD(c);
+    return rows_gather(c, nrows, rows, k, Y, ldy, X, ldx);
+}
+int sfem_dgemm_lower(sfem_ctx* c, int opA, int opB, int n, int64_t K, double alpha, const double* A, int64_t lda, const double* B,
+                     int64_t ldb, double beta, double* C, int64_t ldc) {
+    GUARD(c);
+    if (n < 0 || K < 0 || !A || !B || !C) return sfem_fail(c, SFEM_ERR_ARG, "dgemm_lower: bad arguments");
+    return dgemm(c, opA, opB, n, n, K, alpha, A, lda, B, ldb, beta, C, ldc, 1);
+}
+int sfem_mirror_lower(sfem_ctx* c, int n, double* A, int64_t lda) {
+    GUARD(c);
+    return mirror_lower(c, n, A, lda);
+}
+
 int sfem_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z) {
     GUARD(c);
     return dense_axpby(c, n, a, x, b, y, z);

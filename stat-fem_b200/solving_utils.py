@@ -14,7 +14,7 @@ from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
 
 _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_size", "mg_nu", "mg_omega", "mg_omega2",
-                      "mg_max_coarse", "workspace_gb"}
+                      "mg_max_coarse", "workspace_gb", "symmetric_split"}
 
 
 def _lattice_nodes(coords, bbox=None):
@@ -83,6 +83,7 @@ class SparseSolver(object):
         self.mg_omega = float(params.get("mg_omega", 0.8))
         self.mg_omega2 = float(params.get("mg_omega2", self.mg_omega))
         self.mg_max_coarse = int(params.get("mg_max_coarse", 600))
+        self.symmetric_split = bool(params.get("symmetric_split", True))
         self.n = A.shape[0]
         self.ctx = _lib.new_context()
         self._work = None
@@ -249,6 +250,28 @@ def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_by
     return ensemble_comm.gather_rows_to_root(res.contiguous(), [b - a for a, b in rcounts])
 
 
+def _symmetric_split_wtz(ctx, lib, G, W, Z, n, k):
+    """W^T Z for W = G Z on one process, using G = S + E (E: entries without a stored transpose, csrc/symsplit.cu):
+    (S Z)^T Z is symmetric, so only the tiles on and below the diagonal are computed and mirrored; (E Z)^T Z is a GEMM
+    over the few non-empty rows of E.  W is overwritten with S Z."""
+    rows, E = G.unsymmetric_part()
+    ne = int(rows.shape[0])
+    res = ctx.empty((k, k))
+    if ne:
+        We = E.matmul(Z)                                             # (ne x k): rows of E Z
+        ctx.check(lib.sfem_rows_axpy(ctx.handle, ne, _lib.ptr(rows), k, -1.0, _lib.ptr(We), int(We.stride(0)),
+                                     _lib.ptr(W), int(W.stride(0))))          # W <- S Z
+    ctx.check(lib.sfem_dgemm_lower(ctx.handle, _lib.OP_T, _lib.OP_N, k, n, 1.0, _lib.ptr(W), int(W.stride(0)),
+                                   _lib.ptr(Z), int(Z.stride(0)), 0.0, _lib.ptr(res), k))
+    ctx.check(lib.sfem_mirror_lower(ctx.handle, k, _lib.ptr(res), k))
+    if ne:
+        Ze = ctx.empty((ne, k))
+        ctx.check(lib.sfem_rows_gather(ctx.handle, ne, _lib.ptr(rows), k, _lib.ptr(Z), int(Z.stride(0)), _lib.ptr(Ze), k))
+        ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, k, k, ne, 1.0, _lib.ptr(We), int(We.stride(0)),
+                                 _lib.ptr(Ze), k, 1.0, _lib.ptr(res), k))
+    return res
+
+
 def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF, return_device=False):
     """Phi_l^T A^-1 G A^-1 Phi_r on the root process, ``(0, 0)`` elsewhere (solving_utils.py:61-169).
 
@@ -298,7 +321,10 @@ def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF,
         ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, int(Wb.shape[1]), int(Zb.shape[1]), int(Wb.shape[0]), 1.0,
                                  _lib.ptr(Wb), int(Wb.stride(0)), _lib.ptr(Zb), int(Zb.stride(0)), beta,
                                  _lib.ptr(out), int(out.stride(0))))
-    full = sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, ctx.zeros)
+    if size == 1 and same and nloc >= 256 and ls.symmetric_split:
+        full = _symmetric_split_wtz(ctx, lib, G, Wr, Zr, n, nloc)
+    else:
+        full = sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, ctx.zeros)
     if im_left.comm.rank == 0 and rank == 0:
         out = full.reshape(-1).reshape(n_left, n_right)      # the reference's reshape (lines 164-169)
         return out if return_device else out.cpu().numpy()

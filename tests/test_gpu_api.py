@@ -255,3 +255,34 @@ def test_snapshots_concurrent_fit_and_block_posterior_means():
         xr = fem.Function(V)
         a.solve_posterior(xr, scale_mean=False)
         assert relerr(x.data, xr.data) < TOL
+
+
+def test_symmetric_split_covariance_assembly():
+    """Cu = (G Z)^T Z assembled as (S Z)^T Z [lower tiles, mirrored] + (E Z)^T Z must equal the plain GEMM: G is
+    structurally non-symmetric next to the boundary (SURVEY finding 1) and that asymmetry has to survive the split."""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    nodes = 129
+    V, A, b = fem.poisson_problem(nodes, 2)
+    h = 1. / (nodes - 1)
+    sig, l = np.log(2.e-2), np.log(1.5 * h)
+    reg = 1.e-8 * h ** 4 * np.exp(2 * sig)
+    s = np.random.default_rng(11).uniform(0.01, 0.99, (300, 2))      # sensors close to the boundary included
+    od = stat_fem.ObsData(s, np.zeros(300), 2.e-3)
+    G = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg)
+    rows, E = G.unsymmetric_part()
+    assert rows.shape[0] > 0 and E.nnz > 0, "this mesh must have unmatched entries next to the boundary"
+    ip, ix, v = G.G.to_host()
+    Gs = sp.csr_matrix((v, ix, ip), shape=(V.dim(), V.dim()))
+    Eh = sp.csr_matrix((E.data.cpu().numpy(), E.indices.cpu().numpy(), E.indptr.cpu().numpy()), shape=(rows.shape[0], V.dim()))
+    Efull = sp.lil_matrix(Gs.shape)
+    Efull[rows.cpu().numpy()] = Eh
+    S = (Gs - Efull.tocsr())
+    assert abs(S - S.T).max() == 0., "G - E must be exactly symmetric"
+    D = (Gs - Gs.T).tocsr(); D.eliminate_zeros()
+    assert D.nnz == 2 * E.nnz
+    Cu_split = stat_fem.LinearSolver(A, b, G, od).solve_prior()[1]
+    Cu_plain = stat_fem.LinearSolver(A, b, G, od, solver_parameters={"symmetric_split": False}).solve_prior()[1]
+    assert relerr(Cu_split, Cu_plain) < 1e-12
+    asym = np.max(np.abs(Cu_plain - Cu_plain.T))
+    assert asym > 0. and np.max(np.abs((Cu_split - Cu_split.T) - (Cu_plain - Cu_plain.T))) < 1e-10 * asym + 1e-14 * np.max(np.abs(Cu_plain))
