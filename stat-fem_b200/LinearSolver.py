@@ -448,17 +448,41 @@ def solve_posterior_snapshots(solvers, xs, scale_mean=False):
         sfs = [r if scale_mean else 1. for r in rhos]
 
         def dense_cols(rho2s, with_Cu, rhs_cols):
+            """one dense data-space solve per snapshot; clones with a private stream run theirs concurrently (one host
+            thread each), the others one after the other on the main stream"""
+            import threading
             out = ctx.empty((nobs, ns))
             ctx.sync()                   # right-hand sides were produced on the main stream; clones may use their own
-            for s, ls in enumerate(sub):
+            cols, errs = [None] * ns, [None] * ns
+
+            def one(s_, use_stream):
                 try:
-                    col = ls._dense_solve(rho2s[s], with_Cu, rhs_cols[s])
-                except LinAlgError:
+                    if use_stream:
+                        with torch.cuda.stream(sub[s_].dctx.tstream):
+                            cols[s_] = sub[s_]._dense_solve(rho2s[s_], with_Cu, rhs_cols[s_])
+                            sub[s_].dctx.sync()
+                    else:
+                        cols[s_] = sub[s_]._dense_solve(rho2s[s_], with_Cu, rhs_cols[s_])
+                except BaseException as exc:
+                    errs[s_] = exc
+
+            threads = [threading.Thread(target=one, args=(s_, True)) for s_ in range(ns) if sub[s_].dctx.tstream is not None]
+            for t in threads:
+                t.start()
+            for s_ in range(ns):
+                if sub[s_].dctx.tstream is None:
+                    one(s_, False)
+            for t in threads:
+                t.join()
+            for exc in errs:
+                if isinstance(exc, LinAlgError):
                     raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy" +
                                       (" plus forcing covariance" if with_Cu else ""))
-                if ls.dctx is not ctx:
-                    ls.dctx.sync()
-                out[:, s] = col
+                if exc is not None:
+                    raise exc
+            ctx.sync()
+            for s_ in range(ns):
+                out[:, s_] = cols[s_]
             return out
 
         def aga(M):      # A^-1 G A^-1 on a block of columns, Dirichlet lifting off (solving_utils.py:46-57)
