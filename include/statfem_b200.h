@@ -127,6 +127,16 @@ int sfem_rows_gather(sfem_ctx* ctx, int64_t nrows, const int32_t* rows, int k, c
 int sfem_dgemm_lower(sfem_ctx* ctx, int opA, int opB, int n, int64_t K, double alpha, const double* A, int64_t lda,
                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 int sfem_mirror_lower(sfem_ctx* ctx, int n, double* A, int64_t lda);
+/* Self-check hook of the staged-tile operators (csrc/tileop.cu): applies ONE operator of the multigrid hierarchy built
+ * by sfem_mg_setup -- which: 0 = level operator, 1 = prolongation from level+1, 2 = restriction to level+1; mode: 0 Y=AX,
+ * 1 Y+=AX, 2 Y=AX with dot(X,Y), 3 Jacobi sweep, 4 Jacobi sweep with dot(B,Y), 5 residual B-AX, 6 two sweeps from zero --
+ * in that level's tile numbering, with the FP64 tensor-core (DMMA) form of the operator switched on or off, so that
+ * tests can compare the two kernel families on the same data.  X: cols x k, B / Y: rows x k (leading dimension k),
+ * partials: 1184 x k per-CTA dot partials of which *nparts_out_host rows are written.  With k = 0 only the shape and
+ * the number of k-tile records per chunk (0: tensor form not built for this operator) are reported. */
+int sfem_tile_apply_one(sfem_ctx* ctx, int level, int which, int mode, int k, const double* X, const double* B, double* Y,
+                        double* partials, int* nparts_out_host, int use_tensor_form, int64_t* rows_out_host,
+                        int64_t* cols_out_host, int* tensor_form_out_host);
 size_t sfem_potrf_dinv_doubles(int n);
 /* In-place lower Cholesky of the row-major n x n matrix A (only the lower triangle is read); dinv receives the
  * inverses of the 128x128 diagonal blocks.  info_out_host: 0 or the 1-based index of the first non-positive pivot. */

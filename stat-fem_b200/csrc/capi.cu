@@ -26,6 +26,8 @@ int unsym_count(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, 
                 int64_t* eptr_full, int64_t* rowpos, int64_t* nrows_host, int64_t* nnz_host);
 int unsym_fill(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, const int64_t* eptr_full,
                const int64_t* rowpos, int32_t* rows_out, int64_t* eptr_out, int32_t* eidx_out, double* eval_out);
+int mg_tile_apply_one(sfem_ctx* c, int level, int which, int mode, int k, const double* X, const double* B, double* Y,
+                      double* partials, int* nparts_host, int use_dmma, int64_t* rows_out, int64_t* cols_out, int* has_dmma_out);
 int rows_axpy(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx, double* Y, int64_t ldy);
 int rows_gather(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X, int64_t ldx);
 int mirror_lower(sfem_ctx* c, int n, double* A, int64_t ld);
@@ -72,6 +74,7 @@ int sfem_create(sfem_ctx** out, int device, void* cuda_stream) {
     c->stream = (cudaStream_t)cuda_stream;
     if (const char* e = getenv("SFEM_TILE_ROWS")) c->tile_rows = atoi(e);     // tuning knobs of the staged-tile kernels
     if (const char* e = getenv("SFEM_TILE_SW")) c->tile_sw = atoi(e);
+    if (const char* e = getenv("SFEM_TILE_DMMA")) c->tile_dmma = atoi(e);
     if (cudaMallocHost(&c->pinned, 4096) != cudaSuccess) {
         delete c;
         return SFEM_ERR_CUDA;
@@ -255,6 +258,13 @@ int sfem_dgemm_lower(sfem_ctx* c, int opA, int opB, int n, int64_t K, double alp
     GUARD(c);
     if (n < 0 || K < 0 || !A || !B || !C) return sfem_fail(c, SFEM_ERR_ARG, "dgemm_lower: bad arguments");
     return dgemm(c, opA, opB, n, n, K, alpha, A, lda, B, ldb, beta, C, ldc, 1);
+}
+int sfem_tile_apply_one(sfem_ctx* c, int level, int which, int mode, int k, const double* X, const double* B, double* Y,
+                        double* partials, int* nparts_out_host, int use_tensor_form, int64_t* rows_out_host,
+                        int64_t* cols_out_host, int* tensor_form_out_host) {
+    GUARD(c);
+    return mg_tile_apply_one(c, level, which, mode, k, X, B, Y, partials, nparts_out_host, use_tensor_form, rows_out_host,
+                             cols_out_host, tensor_form_out_host);
 }
 int sfem_mirror_lower(sfem_ctx* c, int n, double* A, int64_t lda) {
     GUARD(c);

@@ -56,6 +56,7 @@ struct sfem_ctx {
     double mg_omega2 = 0.8;          // weight of every second sweep (== mg_omega: plain damped Jacobi)
     int tile_rows = 0;               // rows per fine-level chunk of the staged-tile operators (0: default)
     int tile_sw = 0;                 // slab width override for the tile kernels (0: automatic, 32: force 32 columns)
+    int tile_dmma = 1;               // FP64 tensor-core form of the staged-tile operators (0: scalar kernels only)
 
     // ---- optional per-kernel-family timing (CUDA events on the launch stream) + algorithmic work counters ------
     unsigned prof_mask = 0;

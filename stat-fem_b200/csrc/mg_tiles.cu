@@ -474,6 +474,32 @@ int mg_build_tiles(sfem_ctx* c) {
 
 const int* mg_tiles_fine_perm(sfem_ctx* c) { return c->mg.empty() ? nullptr : c->mg[0]->perm; }
 
+// Apply ONE operator of the hierarchy (which: 0 = level operator A_l, 1 = prolongation P_l, 2 = restriction R_l) in the
+// level's tile numbering, with the tensor-core form switched on or off: the check that both kernel families agree
+// (tests/test_gpu_kernels.py).  X: [cols x k], B and Y: [rows x k], all with leading dimension k; partials:
+// [TILE_MAX_PARTS x k] (dot modes), *nparts_host rows of it are written.  rows_out / cols_out (nullable) report the shape.
+int mg_tile_apply_one(sfem_ctx* c, int level, int which, int mode, int k, const double* X, const double* B, double* Y,
+                      double* partials, int* nparts_host, int use_dmma, int64_t* rows_out, int64_t* cols_out, int* has_dmma_out) {
+    if (level < 0 || level >= (int)c->mg.size()) return sfem_fail(c, SFEM_ERR_ARG, "tile_apply_one: no such level");
+    MGLevel* L = c->mg[level];
+    const TileOp& op = which == 0 ? L->tA : (which == 1 ? L->tP : L->tR);
+    if (rows_out) *rows_out = op.nrows;
+    if (cols_out) *cols_out = op.ncols;
+    if (has_dmma_out) *has_dmma_out = op.kts > 0 ? op.kts : 0;
+    if (k <= 0 || !X || !Y) return SFEM_OK;
+    if (op.nrows <= 0) return sfem_fail(c, SFEM_ERR_STATE, "tile_apply_one: operator not built on this level");
+    TileArgs a;
+    a.k = k; a.X = X; a.ldx = k; a.Y = Y; a.ldy = k; a.B = B; a.ldb = k;
+    a.dinv = L->dinv_t; a.dinv2 = L->dinv_t2; a.partials = partials;
+    const int saved = c->tile_dmma;
+    c->tile_dmma = use_dmma;
+    int np = 0;
+    int rc = tileop_apply(c, TAG_SETUP, op, mode, a, 0.0, &np);
+    c->tile_dmma = saved;
+    if (nparts_host) *nparts_host = np;
+    return rc;
+}
+
 // workspace: for every lattice level: x0, x1, b  (each n_l x k)
 size_t mg_tiles_workspace_bytes(sfem_ctx* c, int k) {
     size_t bytes = 0;

@@ -158,9 +158,118 @@ __global__ void tile_scale_kernel(int nchunks, int dl, int n4, int e8, const int
     }
 }
 
+// ------------------------------------------------------------------------------------------------ DMMA form
+// One thread per chunk.  For each group of 8 consecutive rows the distinct staged slots with a nonzero entry are
+// binned by (slot mod 4); k-tile t of the group takes the t-th slot of every bin (a bin that has run out is padded
+// with a staged slot of the same residue and an all-zero block column), so that the four rows of a B fragment always
+// sit in different 32-byte bank groups of the swizzled stage buffer.
+constexpr int TD_BIN = 48;        // slots of one residue a row group may touch
+
+struct TdBins {
+    unsigned short slot[4][TD_BIN];
+    int cnt[4];
+};
+
+// bins of row group [row0, row1) of a chunk with ELL width W; returns false on overflow
+__device__ bool td_bins(const unsigned short* __restrict__ ec, const double* __restrict__ pat, int W, int row0, int row1, TdBins& b) {
+    b.cnt[0] = b.cnt[1] = b.cnt[2] = b.cnt[3] = 0;
+    for (int r = row0; r < row1; ++r)
+        for (int w = 0; w < W; ++w) {
+            if (pat[r * W + w] == 0.0) continue;
+            const unsigned short s = ec[r * W + w];
+            const int q = s & 3;
+            bool found = false;
+            for (int i = 0; i < b.cnt[q]; ++i) found |= (b.slot[q][i] == s);
+            if (found) continue;
+            if (b.cnt[q] == TD_BIN) return false;
+            b.slot[q][b.cnt[q]++] = s;
+        }
+    return true;
+}
+
+// stats[0] = max k-tiles per chunk, stats[1] = max nonzeros per chunk, stats[2] = not representable, stats[3] = max k-tiles per row group
+__global__ void tile_dmma_count_kernel(int nchunks, int dl, int e8, const int* __restrict__ desc, const unsigned short* __restrict__ ecol,
+                                       const double* __restrict__ eval, int* __restrict__ stats) {
+    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= nchunks) return;
+    const int* dsc = desc + (size_t)cidx * dl;
+    const int nr = dsc[1], W = dsc[3];
+    const unsigned short* ec = ecol + (size_t)cidx * e8;
+    const double* ev = eval + (size_t)cidx * e8;
+    if (nr > 32) { stats[2] = 1; return; }
+    TdBins b;
+    int tiles = 0, nz = 0;
+    for (int g = 0; g < 4; ++g) {
+        const int row0 = g * 8, row1 = min(row0 + 8, nr);
+        if (row0 >= row1) break;
+        if (!td_bins(ec, ev, W, row0, row1, b)) { stats[2] = 1; return; }
+        const int kt = max(max(b.cnt[0], b.cnt[1]), max(b.cnt[2], b.cnt[3]));
+        tiles += kt;
+        atomicMax(&stats[3], kt);
+        for (int t = row0 * W; t < row1 * W; ++t) nz += (ev[t] != 0.0);
+    }
+    atomicMax(&stats[0], tiles);
+    atomicMax(&stats[1], nz);
+}
+
+// write_meta: also fills the k-tile records and desc[6]; pat decides which entries exist, src supplies their values
+__global__ void tile_dmma_fill_kernel(int nchunks, int dl, int e8, int kts, int ap8, int write_meta, int* __restrict__ desc,
+                                      const unsigned short* __restrict__ ecol, const double* __restrict__ pat,
+                                      const double* __restrict__ src, uint4* __restrict__ ktmeta, double* __restrict__ apack) {
+    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cidx >= nchunks) return;
+    int* dsc = desc + (size_t)cidx * dl;
+    const int nr = dsc[1], nneed = dsc[2], W = dsc[3];
+    const unsigned short* ec = ecol + (size_t)cidx * e8;
+    const double* pt = pat + (size_t)cidx * e8;
+    const double* sv = src + (size_t)cidx * e8;
+    uint4* meta = ktmeta + (size_t)cidx * kts;
+    double* ap = apack + (size_t)cidx * ap8;
+    TdBins b;
+    int tile = 0, base = 0;
+    unsigned counts = 0;
+    for (int g = 0; g < 4; ++g) {
+        const int row0 = g * 8, row1 = min(row0 + 8, nr);
+        if (row0 >= row1) break;
+        td_bins(ec, pt, W, row0, row1, b);
+        const int KT = max(max(b.cnt[0], b.cnt[1]), max(b.cnt[2], b.cnt[3]));
+        counts |= (unsigned)KT << (8 * g);
+        unsigned short any = 0;
+        for (int q = 0; q < 4; ++q)
+            if (b.cnt[q]) any = b.slot[q][0];
+        for (int t = 0; t < KT; ++t) {
+            unsigned short sl[4];
+            for (int q = 0; q < 4; ++q) sl[q] = t < b.cnt[q] ? b.slot[q][t] : (unsigned short)(q < nneed ? q : any);
+            unsigned mask = 0;
+            const int first = base;
+            for (int lr = 0; lr < 8; ++lr) {
+                const int r = row0 + lr;
+                if (r >= row1) break;
+                for (int q = 0; q < 4; ++q) {
+                    if (t >= b.cnt[q]) continue;
+                    double sum = 0.0;
+                    bool has = false;
+                    for (int w = 0; w < W; ++w)
+                        if (pt[r * W + w] != 0.0 && ec[r * W + w] == sl[q]) { sum += sv[r * W + w]; has = true; }
+                    if (has) {
+                        mask |= 1u << (lr * 4 + q);
+                        ap[base++] = sum;
+                    }
+                }
+            }
+            if (write_meta) meta[tile] = make_uint4((unsigned)sl[0] | ((unsigned)sl[1] << 16), (unsigned)sl[2] | ((unsigned)sl[3] << 16), mask, (unsigned)first);
+            ++tile;
+        }
+    }
+    if (write_meta) dsc[6] = (int)counts;
+}
+
 // ------------------------------------------------------------------------------------------------ apply
 struct TileDev {
     const int* desc; const int* need; const unsigned short* ecol; const double* eval;
+    const uint4* ktmeta; const double* apack;
+    int kts, ap8, nst;               // nst: stage buffers of the tensor-core kernel (2 or 3)
+    unsigned off_dacc;
     int nchunks, R, dl, n4, e8;
     // shared-memory geometry (bytes)
     unsigned cb_bytes, st_bytes, off_bs, off_drow, off_red;
@@ -417,6 +526,302 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+// ---- FP64 tensor-core variant -----------------------------------------------------------------------------------
+// The chunk matrix is applied with DMMA m8n8k4.  Warp w owns row group (w & 3) -- 8 rows -- and the 32 columns of half
+// (w >> 2) of a 64-column slab, i.e. four 8x8 accumulator tiles; a staged value is read from shared memory once per
+// k-tile that contains its slot (for all 8 rows of the group) instead of once per matrix entry.
+//
+// Work items run chunk-major: all column slabs of a chunk one after the other.  At the first slab every lane loads its
+// entries of the row group's 8x4 blocks (lane mask + popcount into the packed values) and the slot offsets into
+// REGISTERS, where they stay for the chunk's remaining slabs; the chunk record itself is fetched once per chunk.
+// Staging is done by the TMA engine: one `cp.async.bulk` per input row (512 bytes), dealt out over the warps and
+// completing on the mbarrier of the stage, 2 or 3 stages deep; records travel the same way through a ring of four
+// buffers.  Rows are pitched 544 bytes apart, so the four rows of a B fragment --
+// slots with distinct (slot mod 4) by construction -- fall into different 32-byte bank groups without any swizzle.
+// Dot products (TM_MULT_DOT / TM_JACOBI_DOT) are transposed through a per-warp scratch and accumulated per column in
+// shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
+constexpr int DM_PITCH = 544;     // bytes between staged rows (512 + 32)
+constexpr int DM_KTR = 10;        // k-tiles of a row group held in registers
+constexpr int DM_NREC = 4;        // chunk-record ring
+constexpr int DM_HDR = 64;        // mbarriers: full[3] at 0, record[4] at 24
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16; both addresses 16-byte aligned), completing on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];\n" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArgs a) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    constexpr bool HAS_B = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
+    constexpr bool HAS_D = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
+    constexpr bool NEED_SELF = (MODE == TM_MULT_DOT || MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
+    constexpr bool HAS_DOT = (MODE == TM_MULT_DOT || MODE == TM_JACOBI_DOT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int rg = warp & 3, cpart = warp >> 2;
+    const int NST = op.nst;
+    const int nslab = (a.k + 63) >> 6;
+    const int nmine = ((int)op.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int T = nmine * nslab;
+    const unsigned last_bytes = (unsigned)(a.k - (nslab - 1) * 64) * 8u;      // bytes of a row inside the last slab
+    const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
+    const unsigned rec_a = sm_a + DM_HDR;
+    const unsigned st_a = rec_a + DM_NREC * op.cb_bytes;
+    unsigned char* rec0 = sm + DM_HDR;
+    const unsigned colb = (unsigned)(cpart * 32 + lr) * 8u;                     // this lane's B column inside a staged row
+    const unsigned cole = (unsigned)(cpart * 32 + 2 * lk) * 8u;                 // first of its two C columns (tile g: + 64 g)
+    double* scr = reinterpret_cast<double*>(sm + op.off_red) + warp * 256;     // [8 rows][32 columns] transposition scratch
+    double* dacc = reinterpret_cast<double*>(sm + op.off_dacc);                // [8 warps][nslab][32] column sums
+
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s) mbar_init(sm_a + 8 * s, 1);
+        for (int b = 0; b < DM_NREC; ++b) mbar_init(sm_a + 24 + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (HAS_DOT)
+        for (int i = tid; i < 8 * nslab * 32; i += 256) dacc[i] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+
+    // record of chunk ordinal j into ring buffer j & 3 (one thread: expect, then the four pieces)
+    auto request_record = [&](int j) {
+        if (j >= nmine || tid != 0) return;
+        const size_t cidx = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+        const unsigned bar = sm_a + 24 + 8 * (j & 3);
+        unsigned dst = rec_a + (unsigned)(j & 3) * op.cb_bytes;
+        mbar_expect_tx(bar, op.cb_bytes);
+        bulk_g2s(dst, op.desc + cidx * op.dl, (unsigned)op.dl * 4u, bar);
+        dst += (unsigned)op.dl * 4u;
+        bulk_g2s(dst, op.need + cidx * op.n4, (unsigned)op.n4 * 4u, bar);
+        dst += (unsigned)op.n4 * 4u;
+        bulk_g2s(dst, op.ktmeta + cidx * op.kts, (unsigned)op.kts * 16u, bar);
+        dst += (unsigned)op.kts * 16u;
+        bulk_g2s(dst, op.apack + cidx * op.ap8, (unsigned)op.ap8 * 8u, bar);
+    };
+    auto wait_record = [&](int j) { mbar_wait(sm_a + 24 + 8 * (j & 3), (unsigned)(j >> 2) & 1u); };
+    auto record = [&](int j) { return reinterpret_cast<const int*>(rec0 + (size_t)(j & 3) * op.cb_bytes); };
+    // input rows of item u = (chunk ordinal ju, slab su) into stage `stage`: one bulk copy per row.  cp.async.bulk is a
+    // uniform-datapath instruction (the lanes of a warp issue theirs one after the other), so the rows are dealt out
+    // over all eight warps, at most eight lanes each.
+    auto issue_rows = [&](int ju, int su, int stage) {
+        if (su == 0) wait_record(ju);      // every warp issues for every item, so it has observed the record since slab 0
+        const int* dsc = record(ju);
+        const int* need = dsc + op.dl;
+        const int nneed = dsc[2];
+        const unsigned rb = (su == nslab - 1) ? last_bytes : 512u;
+        const unsigned bar = sm_a + 8 * stage;
+        const unsigned dst = st_a + (unsigned)stage * op.st_bytes;
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)nneed * rb);
+        const double* Xc = a.X + su * 64;
+        for (int ss = warp + 8 * lane; ss < nneed; ss += 256) bulk_g2s(dst + (unsigned)ss * DM_PITCH, Xc + (int64_t)need[ss] * a.ldx, rb, bar);
+    };
+
+    for (int j = 0; j < DM_NREC; ++j) request_record(j);
+    // producer cursor: item u = t + NST - 1
+    int u = 0, uj = 0, us = 0, ustage = 0;
+    for (; u < NST - 1 && u < T; ++u) {
+        issue_rows(uj, us, ustage);
+        if (++us == nslab) { us = 0; ++uj; }
+        if (++ustage == NST) ustage = 0;
+    }
+    wait_record(0);
+
+    // right-hand side / scaling values of this lane's outputs, fetched one item ahead
+    double bq[4][2], di = 0.0, di2 = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bq[g][0] = bq[g][1] = 0.0;
+    auto prefetch_b = [&](int r0n, int nrn, int sn) {
+        const int r = rg * 8 + lr;
+        const bool valid = r < nrn;
+        if (HAS_D) {
+            di = valid ? a.dinv[r0n + r] : 0.0;
+            if (MODE == TM_PRESMOOTH2) di2 = valid ? a.dinv2[r0n + r] : 0.0;
+        }
+        if (HAS_B) {
+            const double* Bc = (MODE == TM_MULT_ADD) ? a.Y : a.B;
+            const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
+            const double* p = Bc + (int64_t)(r0n + r) * lds + sn * 64 + cpart * 32 + 2 * lk;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int col = sn * 64 + cpart * 32 + g * 8 + 2 * lk;
+                bq[g][0] = bq[g][1] = 0.0;
+                if (valid && col < a.k) { const double2 v = *reinterpret_cast<const double2*>(p + g * 8); bq[g][0] = v.x; bq[g][1] = v.y; }
+            }
+        }
+    };
+    {
+        const int* d0 = record(0);
+        prefetch_b(d0[0], d0[1], 0);
+    }
+
+    double av[DM_KTR];
+    unsigned so[DM_KTR];
+    int nkt = 0, r0 = 0, nr = 0;
+    unsigned selfoff = 0xffffffffu;
+    int j = 0, slab = 0, cstage = 0;
+    unsigned cpar = 0;
+    for (int t = 0; t < T; ++t) {
+        if (u < T) {
+            issue_rows(uj, us, ustage);
+            ++u;
+            if (++us == nslab) { us = 0; ++uj; }
+            if (++ustage == NST) ustage = 0;
+        }
+        if (slab == 0) {        // new chunk: block entries and slot offsets of this warp's row group into registers
+            const int* dsc = record(j);
+            r0 = dsc[0]; nr = dsc[1];
+            const unsigned counts = (unsigned)dsc[6];
+            nkt = (int)((counts >> (8 * rg)) & 0xffu);
+            int kt0 = 0;
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+                if (g < rg) kt0 += (int)((counts >> (8 * g)) & 0xffu);
+            const uint4* meta = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(dsc) + (size_t)(op.dl + op.n4) * 4) + kt0;
+            const double* ap = reinterpret_cast<const double*>(meta - kt0 + op.kts);
+            const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+            for (int i = 0; i < DM_KTR; ++i) {
+                av[i] = 0.0; so[i] = colb;
+                if (i < nkt) {
+                    const uint4 m = meta[i];
+                    const unsigned pr = (lk & 2) ? m.y : m.x;
+                    const unsigned slot = (lk & 1) ? (pr >> 16) : (pr & 0xffffu);
+                    so[i] = slot * DM_PITCH + colb;
+                    if ((m.z >> lane) & 1u) av[i] = ap[m.w + __popc(m.z & below)];
+                }
+            }
+            selfoff = 0xffffffffu;
+            if (NEED_SELF && rg * 8 + lr < nr) {
+                const unsigned sl = reinterpret_cast<const unsigned short*>(dsc + 8)[rg * 8 + lr];
+                if (sl != 0xffffu) selfoff = sl * DM_PITCH + cole;
+            }
+        }
+        const unsigned stg = st_a + (unsigned)cstage * op.st_bytes;
+        mbar_wait(sm_a + 8 * cstage, cpar);
+
+        double acc[4][2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.0;
+        double bv[4];
+        {
+            const unsigned ad = stg + so[0];
+            bv[0] = lds_f64<0>(ad); bv[1] = lds_f64<64>(ad); bv[2] = lds_f64<128>(ad); bv[3] = lds_f64<192>(ad);
+        }
+#pragma unroll
+        for (int i = 0; i < DM_KTR; ++i) {
+            if (i < nkt) {
+                double bn[4] = {0.0, 0.0, 0.0, 0.0};
+                if (i + 1 < DM_KTR && i + 1 < nkt) {
+                    const unsigned ad = stg + so[i + 1 < DM_KTR ? i + 1 : i];
+                    bn[0] = lds_f64<0>(ad); bn[1] = lds_f64<64>(ad); bn[2] = lds_f64<128>(ad); bn[3] = lds_f64<192>(ad);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dmma884(acc[g][0], acc[g][1], av[i], bv[g]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) bv[g] = bn[g];
+            }
+        }
+
+        // epilogue: this lane holds row rg*8 + lr, columns cpart*32 + g*8 + 2*lk (+1) of the slab
+        const int r = rg * 8 + lr;
+        const bool rvalid = r < nr;
+        double* Yr = a.Y + (int64_t)(r0 + r) * a.ldy + slab * 64 + cpart * 32 + 2 * lk;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int col = slab * 64 + cpart * 32 + g * 8 + 2 * lk;
+            double s0 = 0.0, s1 = 0.0;
+            if (NEED_SELF && selfoff != 0xffffffffu) {
+                const double2 v = lds_v2f64(stg + selfoff + (unsigned)g * 64u);
+                s0 = v.x; s1 = v.y;
+            }
+            const double a0 = acc[g][0], a1 = acc[g][1], b0 = bq[g][0], b1 = bq[g][1];
+            double y0, y1, p0 = 0.0, p1 = 0.0;
+            if (MODE == TM_MULT) { y0 = a0; y1 = a1; }
+            else if (MODE == TM_MULT_ADD) { y0 = b0 + a0; y1 = b1 + a1; }
+            else if (MODE == TM_MULT_DOT) { y0 = a0; y1 = a1; p0 = s0 * a0; p1 = s1 * a1; }
+            else if (MODE == TM_RESID) { y0 = b0 - a0; y1 = b1 - a1; }
+            else if (MODE == TM_PRESMOOTH2) { y0 = fma(di2, s0 - a0, di * s0); y1 = fma(di2, s1 - a1, di * s1); }
+            else {
+                y0 = fma(di, b0 - a0, s0); y1 = fma(di, b1 - a1, s1);
+                if (MODE == TM_JACOBI_DOT) { p0 = b0 * y0; p1 = b1 * y1; }
+            }
+            const bool ok = rvalid && col < a.k;
+            if (ok) *reinterpret_cast<double2*>(Yr + g * 8) = make_double2(y0, y1);
+            if (HAS_DOT) *reinterpret_cast<double2*>(scr + lr * 32 + g * 8 + 2 * lk) = ok ? make_double2(p0, p1) : make_double2(0.0, 0.0);
+        }
+        if (HAS_DOT) {
+            __syncwarp();
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += scr[q * 32 + lane];
+            dacc[(warp * nslab + slab) * 32 + lane] += s;
+            __syncwarp();
+        }
+
+        // next item: its right-hand side rows (a new chunk's row range comes from the next record)
+        int jn = j, sn = slab + 1;
+        if (sn == nslab) { sn = 0; jn = j + 1; }
+        if (t + 1 < T) {
+            int r0n = r0, nrn = nr;
+            if (sn == 0) {
+                wait_record(jn);
+                const int* dn = record(jn);
+                r0n = dn[0]; nrn = dn[1];
+            }
+            prefetch_b(r0n, nrn, sn);
+        }
+        __syncthreads();
+        if (sn == 0) request_record(j + DM_NREC);      // every reader of record j is done
+        j = jn; slab = sn;
+        if (++cstage == NST) { cstage = 0; cpar ^= 1u; }
+    }
+    if (HAS_DOT) {
+        for (int i = tid; i < nslab * 64; i += 256) {
+            const int sl = i >> 6, c = i & 63, cp = c >> 5, cc = c & 31;
+            double s = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) s += dacc[((cp * 4 + g) * nslab + sl) * 32 + cc];
+            const int col = sl * 64 + c;
+            if (col < a.k) a.partials[(size_t)blockIdx.x * a.k + col] = s;
+        }
+    }
+}
+
 // Fallback for operators whose chunk working set does not fit in shared memory (e.g. wide 3-D transfer operators):
 // same format, rows gathered straight from global memory (warp per row, lanes across 32 columns, slabs looped).
 template <int MODE>
@@ -519,6 +924,43 @@ int launch_kernel(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, i
     return SFEM_OK;
 }
 
+// shared-memory geometry of tileop_dmma_kernel with `nst` stage buffers for k columns; returns the total bytes
+size_t tile_layout_dmma(const TileOp& op, int mode, int k, int nst, TileDev* d) {
+    bool has_dot = (mode == TM_MULT_DOT || mode == TM_JACOBI_DOT);
+    size_t cb = (size_t)op.dl * 4 + (size_t)op.n4 * 4 + (size_t)op.kts * 16 + (size_t)op.ap8 * 8;
+    size_t st = (size_t)op.max_need * DM_PITCH;
+    size_t tot = DM_HDR + DM_NREC * cb + (size_t)nst * st;
+    size_t o_red = tot;
+    if (has_dot) tot += 8 * 256 * sizeof(double);
+    size_t o_dacc = tot;
+    if (has_dot) tot += 8 * (size_t)((k + 63) / 64) * 32 * sizeof(double);
+    if (d) { d->cb_bytes = (unsigned)cb; d->st_bytes = (unsigned)st; d->off_bs = 0; d->off_drow = 0; d->off_red = (unsigned)o_red; d->off_dacc = (unsigned)o_dacc; d->nst = nst; }
+    return tot;
+}
+// stage depth with which two CTAs of tileop_dmma_kernel fit on an SM (0: none)
+int dmma_stages(const TileOp& op, int mode, int k) {
+    for (int nst = 3; nst >= 2; --nst)
+        if (2 * (tile_layout_dmma(op, mode, k, nst, nullptr) + SMEM_RESERVED) <= 227 * 1024) return nst;
+    return 0;
+}
+
+template <int MODE>
+int launch_dmma(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int nst, int* nparts) {
+    size_t smem = tile_layout_dmma(op, MODE, a.k, nst, &d);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tileop_dmma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        attr_set = true;
+    }
+    // persistent grid: two CTAs per SM (register-limited; dmma_stages checked the shared memory)
+    const int64_t want = 2 * (int64_t)SFEM_NUM_SMS;
+    int grid = (int)((int64_t)op.nchunks < want ? (int64_t)op.nchunks : want);
+    if (nparts) *nparts = grid;
+    tileop_dmma_kernel<MODE><<<grid, 256, smem, c->stream>>>(d, a);
+    KCHECK(c);
+    return SFEM_OK;
+}
+
 template <int CW, int VEC, int MODE>
 int launch_variant(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs& a, int* nparts) {
     constexpr bool has_b = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
@@ -532,6 +974,11 @@ int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs&
     bool al2 = (a.ldx % 2 == 0) && (a.ldy % 2 == 0) && (reinterpret_cast<uintptr_t>(a.X) % 16 == 0) &&
                (reinterpret_cast<uintptr_t>(a.Y) % 16 == 0) &&
                (a.B == nullptr || (a.ldb % 2 == 0 && reinterpret_cast<uintptr_t>(a.B) % 16 == 0));
+    // FP64 tensor-core form: wide blocks on operators with 32-row chunks, if two CTAs fit on an SM
+    if (d.kts > 0 && c->tile_dmma && a.k > 32 && a.k % 2 == 0 && al2) {
+        const int nst = dmma_stages(op, MODE, a.k);
+        if (nst) return launch_dmma<MODE>(c, op, d, a, nst, nparts);
+    }
     if (a.k <= 4 && tile_layout(op, MODE, 4, nullptr) <= SMEM_CAP) return launch_variant<4, 1, MODE>(c, op, d, a, nparts);
     if (a.k <= 16 && tile_layout(op, MODE, 16, nullptr) <= SMEM_CAP) return launch_variant<16, 1, MODE>(c, op, d, a, nparts);
     if (a.k > 32 && al2 && c->tile_sw != 32 && 2 * (tile_layout(op, MODE, 64, nullptr) + SMEM_RESERVED) <= 227 * 1024) return launch_variant<32, 2, MODE>(c, op, d, a, nparts);
@@ -549,10 +996,46 @@ int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs&
 
 void tileop_free(TileOp* op) {
     if (!op) return;
-    void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled};
+    void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled, op->ktmeta, op->apack, op->apack_scaled};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *op = TileOp();
+}
+
+// k-tile records and packed block values of the FP64 tensor-core form, from the ELL blocks already on the device.
+// Operators that do not fit the form (a row group touching more than TD_BIN slots of one residue) keep kts = 0.
+static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
+    if (op->nchunks <= 0) return SFEM_OK;
+    int* stats = nullptr;
+    CUDA_TRY(c, cudaMalloc(&stats, sizeof(int) * 4));
+    CUDA_TRY(c, cudaMemsetAsync(stats, 0, sizeof(int) * 4, c->stream));
+    const int tb = 64, nb = (op->nchunks + tb - 1) / tb;
+    {
+        ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
+        tile_dmma_count_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->desc, op->ecol, op->eval, stats);
+        c->launches++;
+    }
+    int h[4] = {0, 0, 0, 0};
+    cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(stats);
+    if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: k-tile count failed: %s", cudaGetErrorString(e));
+    if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DM_KTR) return SFEM_OK;      // the kernel keeps a row group's k-tiles in registers
+    const int kts = h[0], ap8 = h[1] > 0 ? (h[1] + 1) & ~1 : 2;
+    size_t nc = (size_t)op->nchunks;
+    CUDA_TRY(c, cudaMalloc(&op->ktmeta, sizeof(uint4) * nc * kts));
+    CUDA_TRY(c, cudaMalloc(&op->apack, sizeof(double) * nc * ap8));
+    CUDA_TRY(c, cudaMemsetAsync(op->ktmeta, 0, sizeof(uint4) * nc * kts, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(op->apack, 0, sizeof(double) * nc * ap8, c->stream));
+    {
+        ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
+        tile_dmma_fill_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, kts, ap8, 1, op->desc, op->ecol, op->eval, op->eval,
+                                                        op->ktmeta, op->apack);
+        KCHECK(c);
+    }
+    op->kts = kts; op->ap8 = ap8;
+    if (getenv("SFEM_DEBUG")) fprintf(stderr, "tileop dmma form: %d k-tiles, %d values per chunk (%d rows, need %d)\n", kts, ap8, op->max_rows, op->max_need);
+    return SFEM_OK;
 }
 
 int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, const int32_t* idx, const double* val,
@@ -605,6 +1088,7 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
     }
     if (getenv("SFEM_DEBUG")) fprintf(stderr, "tileop %lld x %lld nnz %lld chunks %d R %d need %d W %d dl %d\n", (long long)nrows, (long long)ncols, (long long)nnz, nchunks, max_rows, op.max_need, hstats[1], op.dl);
     *out = op;
+    if (c->tile_dmma && max_rows > 16 && max_rows <= 32) return tileop_build_dmma(c, out);
     return SFEM_OK;
 }
 
@@ -614,6 +1098,14 @@ int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv) {
     ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
     tile_scale_kernel<<<op->nchunks, 128, 0, c->stream>>>(op->nchunks, op->dl, op->n4, op->e8, op->desc, op->need, op->ecol, op->eval, dinv, op->eval_scaled);
     KCHECK(c);
+    if (op->kts > 0) {
+        size_t nc = (size_t)op->nchunks;
+        if (!op->apack_scaled) CUDA_TRY(c, cudaMalloc(&op->apack_scaled, sizeof(double) * nc * op->ap8));
+        CUDA_TRY(c, cudaMemsetAsync(op->apack_scaled, 0, sizeof(double) * nc * op->ap8, c->stream));
+        tile_dmma_fill_kernel<<<(op->nchunks + 63) / 64, 64, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->kts, op->ap8, 0, op->desc, op->ecol,
+                                                                            op->eval, op->eval_scaled, op->ktmeta, op->apack_scaled);
+        KCHECK(c);
+    }
     return SFEM_OK;
 }
 
@@ -627,6 +1119,9 @@ int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArg
     d.eval = (mode == TM_PRESMOOTH2) ? op.eval_scaled : op.eval;
     if (!d.eval) return sfem_fail(c, SFEM_ERR_STATE, "tileop_apply: scaled entries not built");
     d.nchunks = op.nchunks; d.R = op.max_rows; d.dl = op.dl; d.n4 = op.n4; d.e8 = op.e8;
+    d.ktmeta = op.ktmeta; d.kts = op.kts; d.ap8 = op.ap8;
+    d.apack = (mode == TM_PRESMOOTH2) ? op.apack_scaled : op.apack;
+    if (!d.apack) d.kts = 0;
     ProfScope ps(c, tag, bytes, 2.0 * (double)op.nnz * a.k);
     switch (mode) {
         case TM_MULT: return launch_mode<TM_MULT>(c, op, d, a, nparts);

@@ -31,6 +31,15 @@ struct TileOp {
     unsigned short* ecol = nullptr;   // [nchunks][e8]  per-chunk ELL block: row r's W entries at [r*W, r*W + W), zero padded
     double* eval = nullptr;           // [nchunks][e8]
     double* eval_scaled = nullptr;    // [nchunks][e8] a_ij * d_j (square level operators: first sweep folded in), optional
+    // ---- FP64 tensor-core form (chunks of 17..32 rows): every group of 8 rows is cut into k-tiles of 4 staged slots
+    // with distinct (slot mod 4); a k-tile is an 8x4 block of the chunk matrix, multiplied with DMMA m8n8k4.  Only the
+    // nonzeros of a block are stored (lane order), located through a 32-bit lane mask.  desc[6] = k-tile counts of the
+    // four row groups (one byte each).
+    int kts = 0;                      // k-tile records per chunk (stride), 0: form not built
+    int ap8 = 0;                      // packed block values per chunk (stride, even)
+    uint4* ktmeta = nullptr;          // [nchunks][kts] {slot0 | slot1 << 16, slot2 | slot3 << 16, lane mask, first value}
+    double* apack = nullptr;          // [nchunks][ap8]
+    double* apack_scaled = nullptr;   // [nchunks][ap8] from eval_scaled
 };
 
 enum {
