@@ -535,15 +535,16 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
 // entries of the row group's 8x4 blocks (lane mask + popcount into the packed values) and the slot offsets into
 // REGISTERS, where they stay for the chunk's remaining slabs; the chunk record itself is fetched once per chunk.
 // Staging is done by the TMA engine: one `cp.async.bulk` per input row (512 bytes), dealt out over the warps and
-// completing on the mbarrier of the stage, 2 or 3 stages deep; records travel the same way through a ring of four
-// buffers.  Rows are pitched 544 bytes apart, so the four rows of a B fragment --
+// completing on the "full" mbarrier of the stage, 2 or 3 stages deep; a stage is refilled once all eight warps have
+// arrived on its "empty" mbarrier, so the loop has no block-wide barrier.  Records travel the same way through a ring
+// of four buffers.  Rows are pitched 544 bytes apart, so the four rows of a B fragment --
 // slots with distinct (slot mod 4) by construction -- fall into different 32-byte bank groups without any swizzle.
 // Dot products (TM_MULT_DOT / TM_JACOBI_DOT) are transposed through a per-warp scratch and accumulated per column in
 // shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
 constexpr int DM_PITCH = 544;     // bytes between staged rows (512 + 32)
 constexpr int DM_KTR = 10;        // k-tiles of a row group held in registers
 constexpr int DM_NREC = 4;        // chunk-record ring
-constexpr int DM_HDR = 64;        // mbarriers: full[3] at 0, record[4] at 24
+constexpr int DM_HDR = 128;       // mbarriers: full[3] at 0, record[4] at 24, empty[3] at 56, chunk-done[4] at 80
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -555,6 +556,9 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
@@ -609,8 +613,8 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     double* dacc = reinterpret_cast<double*>(sm + op.off_dacc);                // [8 warps][nslab][32] column sums
 
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) mbar_init(sm_a + 8 * s, 1);
-        for (int b = 0; b < DM_NREC; ++b) mbar_init(sm_a + 24 + 8 * b, 1);
+        for (int s = 0; s < 3; ++s) { mbar_init(sm_a + 8 * s, 1); mbar_init(sm_a + 56 + 8 * s, 8); }
+        for (int b = 0; b < DM_NREC; ++b) { mbar_init(sm_a + 24 + 8 * b, 1); mbar_init(sm_a + 80 + 8 * b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (HAS_DOT)
@@ -638,31 +642,39 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     // input rows of item u = (chunk ordinal ju, slab su) into stage `stage`: one bulk copy per row.  cp.async.bulk is a
     // uniform-datapath instruction (the lanes of a warp issue theirs one after the other), so the rows are dealt out
     // over all eight warps, at most eight lanes each.
-    auto issue_rows = [&](int ju, int su, int stage) {
-        if (su == 0) wait_record(ju);      // every warp issues for every item, so it has observed the record since slab 0
-        const int* dsc = record(ju);
-        const int* need = dsc + op.dl;
-        const int nneed = dsc[2];
+    const double* urow = nullptr;      // producer side: this lane's input row of the chunk being requested (slab 0 position)
+    unsigned udst = 0, unn = 0;
+    auto issue_rows = [&](int ju, int su, int stage, unsigned par) {
+        mbar_wait(sm_a + 56 + 8 * stage, par ^ 1u);      // all eight warps have released the stage's previous item
+        if (su == 0) {       // every warp issues for every item, so it has observed the record since slab 0
+            wait_record(ju);
+            const int* dsc = record(ju);
+            unn = (unsigned)dsc[2];
+            const unsigned ss = (unsigned)warp + 8u * (unsigned)lane;      // the builder guarantees at most 64 rows per chunk
+            urow = (lane < 8 && ss < unn) ? a.X + (int64_t)dsc[op.dl + ss] * a.ldx : nullptr;
+            udst = ss * DM_PITCH;
+        }
         const unsigned rb = (su == nslab - 1) ? last_bytes : 512u;
         const unsigned bar = sm_a + 8 * stage;
-        const unsigned dst = st_a + (unsigned)stage * op.st_bytes;
-        if (tid == 0) mbar_expect_tx(bar, (unsigned)nneed * rb);
-        const double* Xc = a.X + su * 64;
-        for (int ss = warp + 8 * lane; ss < nneed; ss += 256) bulk_g2s(dst + (unsigned)ss * DM_PITCH, Xc + (int64_t)need[ss] * a.ldx, rb, bar);
+        if (tid == 0) mbar_expect_tx(bar, unn * rb);
+        if (urow) bulk_g2s(st_a + (unsigned)stage * op.st_bytes + udst, urow + su * 64, rb, bar);
     };
 
     for (int j = 0; j < DM_NREC; ++j) request_record(j);
     // producer cursor: item u = t + NST - 1
     int u = 0, uj = 0, us = 0, ustage = 0;
+    unsigned upar = 0;
     for (; u < NST - 1 && u < T; ++u) {
-        issue_rows(uj, us, ustage);
+        issue_rows(uj, us, ustage, upar);
         if (++us == nslab) { us = 0; ++uj; }
-        if (++ustage == NST) ustage = 0;
+        if (++ustage == NST) { ustage = 0; upar ^= 1u; }
     }
     wait_record(0);
 
     // right-hand side / scaling values of this lane's outputs, fetched one item ahead
     double bq[4][2], di = 0.0, di2 = 0.0;
+    const double* brow = nullptr;      // this lane's right-hand-side row of the chunk being prefetched
+    double* yrow = nullptr;            // its output row of the chunk being computed
 #pragma unroll
     for (int g = 0; g < 4; ++g) bq[g][0] = bq[g][1] = 0.0;
     auto prefetch_b = [&](int r0n, int nrn, int sn) {
@@ -675,12 +687,13 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
         if (HAS_B) {
             const double* Bc = (MODE == TM_MULT_ADD) ? a.Y : a.B;
             const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
-            const double* p = Bc + (int64_t)(r0n + r) * lds + sn * 64 + cpart * 32 + 2 * lk;
+            if (sn == 0) brow = Bc + (int64_t)(r0n + r) * lds + cpart * 32 + 2 * lk;
+            const double* p = brow + sn * 64;
+            const int col0 = sn * 64 + cpart * 32 + 2 * lk;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int col = sn * 64 + cpart * 32 + g * 8 + 2 * lk;
                 bq[g][0] = bq[g][1] = 0.0;
-                if (valid && col < a.k) { const double2 v = *reinterpret_cast<const double2*>(p + g * 8); bq[g][0] = v.x; bq[g][1] = v.y; }
+                if (valid && col0 + g * 8 < a.k) { const double2 v = *reinterpret_cast<const double2*>(p + g * 8); bq[g][0] = v.x; bq[g][1] = v.y; }
             }
         }
     };
@@ -697,10 +710,10 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     unsigned cpar = 0;
     for (int t = 0; t < T; ++t) {
         if (u < T) {
-            issue_rows(uj, us, ustage);
+            issue_rows(uj, us, ustage, upar);
             ++u;
             if (++us == nslab) { us = 0; ++uj; }
-            if (++ustage == NST) ustage = 0;
+            if (++ustage == NST) { ustage = 0; upar ^= 1u; }
         }
         if (slab == 0) {        // new chunk: block entries and slot offsets of this warp's row group into registers
             const int* dsc = record(j);
@@ -725,6 +738,7 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
                     if ((m.z >> lane) & 1u) av[i] = ap[m.w + __popc(m.z & below)];
                 }
             }
+            yrow = a.Y + (int64_t)(r0 + rg * 8 + lr) * a.ldy + cpart * 32 + 2 * lk;
             selfoff = 0xffffffffu;
             if (NEED_SELF && rg * 8 + lr < nr) {
                 const unsigned sl = reinterpret_cast<const unsigned short*>(dsc + 8)[rg * 8 + lr];
@@ -737,30 +751,27 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
         double acc[4][2];
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.0;
-        double bv[4];
+        double bA[4], bB[4];       // B fragments of even / odd k-tiles (static double buffer)
         {
             const unsigned ad = stg + so[0];
-            bv[0] = lds_f64<0>(ad); bv[1] = lds_f64<64>(ad); bv[2] = lds_f64<128>(ad); bv[3] = lds_f64<192>(ad);
+            bA[0] = lds_f64<0>(ad); bA[1] = lds_f64<64>(ad); bA[2] = lds_f64<128>(ad); bA[3] = lds_f64<192>(ad);
         }
 #pragma unroll
         for (int i = 0; i < DM_KTR; ++i) {
-            if (i < nkt) {
-                double bn[4] = {0.0, 0.0, 0.0, 0.0};
-                if (i + 1 < DM_KTR && i + 1 < nkt) {
-                    const unsigned ad = stg + so[i + 1 < DM_KTR ? i + 1 : i];
-                    bn[0] = lds_f64<0>(ad); bn[1] = lds_f64<64>(ad); bn[2] = lds_f64<128>(ad); bn[3] = lds_f64<192>(ad);
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) dmma884(acc[g][0], acc[g][1], av[i], bv[g]);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) bv[g] = bn[g];
+            if (i >= nkt) break;
+            if (i + 1 < DM_KTR) {       // next k-tile's fragments (an unused tile reads column block 0 of slot 0, harmlessly)
+                const unsigned ad = stg + so[i + 1 < DM_KTR ? i + 1 : i];
+                if (i & 1) { bA[0] = lds_f64<0>(ad); bA[1] = lds_f64<64>(ad); bA[2] = lds_f64<128>(ad); bA[3] = lds_f64<192>(ad); }
+                else { bB[0] = lds_f64<0>(ad); bB[1] = lds_f64<64>(ad); bB[2] = lds_f64<128>(ad); bB[3] = lds_f64<192>(ad); }
             }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dmma884(acc[g][0], acc[g][1], av[i], (i & 1) ? bB[g] : bA[g]);
         }
 
         // epilogue: this lane holds row rg*8 + lr, columns cpart*32 + g*8 + 2*lk (+1) of the slab
         const int r = rg * 8 + lr;
         const bool rvalid = r < nr;
-        double* Yr = a.Y + (int64_t)(r0 + r) * a.ldy + slab * 64 + cpart * 32 + 2 * lk;
+        double* Yr = yrow + slab * 64;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int col = slab * 64 + cpart * 32 + g * 8 + 2 * lk;
@@ -805,12 +816,22 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
             }
             prefetch_b(r0n, nrn, sn);
         }
-        __syncthreads();
-        if (sn == 0) request_record(j + DM_NREC);      // every reader of record j is done
+        // release the stage (and, after a chunk's last slab, its record): one arrival per warp -- no block-wide barrier
+        // in the loop, the warps drift up to NST - 1 items apart
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(sm_a + 56 + 8 * cstage);
+            if (sn == 0) mbar_arrive(sm_a + 80 + 8 * (j & 3));
+        }
+        if (sn == 0 && j >= 1 && tid == 0) {     // one chunk later every warp has certainly left record j - 1: refill its buffer
+            mbar_wait(sm_a + 80 + 8 * ((j - 1) & 3), (unsigned)((j - 1) >> 2) & 1u);
+            request_record(j - 1 + DM_NREC);
+        }
         j = jn; slab = sn;
         if (++cstage == NST) { cstage = 0; cpar ^= 1u; }
     }
     if (HAS_DOT) {
+        __syncthreads();
         for (int i = tid; i < nslab * 64; i += 256) {
             const int sl = i >> 6, c = i & 63, cp = c >> 5, cc = c & 31;
             double s = 0.0;
@@ -1020,7 +1041,7 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     cudaFree(stats);
     if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: k-tile count failed: %s", cudaGetErrorString(e));
-    if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DM_KTR) return SFEM_OK;      // the kernel keeps a row group's k-tiles in registers
+    if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DM_KTR || op->max_need > 64) return SFEM_OK;      // the kernel keeps a row group's k-tiles in registers
     const int kts = h[0], ap8 = h[1] > 0 ? (h[1] + 1) & ~1 : 2;
     size_t nc = (size_t)op->nchunks;
     CUDA_TRY(c, cudaMalloc(&op->ktmeta, sizeof(uint4) * nc * kts));
