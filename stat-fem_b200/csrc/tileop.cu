@@ -160,9 +160,10 @@ __global__ void tile_scale_kernel(int nchunks, int dl, int n4, int e8, const int
 
 // ------------------------------------------------------------------------------------------------ DMMA form
 // One thread per chunk.  For each group of 8 consecutive rows the distinct staged slots with a nonzero entry are
-// binned by (slot mod 4); k-tile t of the group takes the t-th slot of every bin (a bin that has run out is padded
-// with a staged slot of the same residue and an all-zero block column), so that the four rows of a B fragment always
-// sit in different 32-byte bank groups of the swizzled stage buffer.
+// binned by (slot mod 4); position q of a k-tile takes the next slot of bin q, so that the four rows of a B fragment
+// sit in different 32-byte bank groups of the (544-byte pitched) stage buffer.  When a bin has run out the position
+// takes a slot of the fullest remaining bin instead -- such a tile pays a 2-way bank conflict, which is cheaper than
+// the extra k-tile (4 DMMAs per warp) a strict assignment would cost: a row group needs ceil(slots / 4) k-tiles.
 constexpr int TD_BIN = 48;        // slots of one residue a row group may touch
 
 struct TdBins {
@@ -203,7 +204,7 @@ __global__ void tile_dmma_count_kernel(int nchunks, int dl, int e8, const int* _
         const int row0 = g * 8, row1 = min(row0 + 8, nr);
         if (row0 >= row1) break;
         if (!td_bins(ec, ev, W, row0, row1, b)) { stats[2] = 1; return; }
-        const int kt = max(max(b.cnt[0], b.cnt[1]), max(b.cnt[2], b.cnt[3]));
+        const int kt = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
         tiles += kt;
         atomicMax(&stats[3], kt);
         for (int t = row0 * W; t < row1 * W; ++t) nz += (ev[t] != 0.0);
@@ -232,21 +233,34 @@ __global__ void tile_dmma_fill_kernel(int nchunks, int dl, int e8, int kts, int 
         const int row0 = g * 8, row1 = min(row0 + 8, nr);
         if (row0 >= row1) break;
         td_bins(ec, pt, W, row0, row1, b);
-        const int KT = max(max(b.cnt[0], b.cnt[1]), max(b.cnt[2], b.cnt[3]));
+        const int KT = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
         counts |= (unsigned)KT << (8 * g);
+        int used[4] = {0, 0, 0, 0};
         unsigned short any = 0;
         for (int q = 0; q < 4; ++q)
             if (b.cnt[q]) any = b.slot[q][0];
         for (int t = 0; t < KT; ++t) {
             unsigned short sl[4];
-            for (int q = 0; q < 4; ++q) sl[q] = t < b.cnt[q] ? b.slot[q][t] : (unsigned short)(q < nneed ? q : any);
+            bool live[4];
+            for (int q = 0; q < 4; ++q) {
+                live[q] = used[q] < b.cnt[q];
+                if (live[q]) sl[q] = b.slot[q][used[q]++];
+            }
+            for (int q = 0; q < 4; ++q) {
+                if (live[q]) continue;
+                int best = -1, rem = 0;
+                for (int p2 = 0; p2 < 4; ++p2)
+                    if (b.cnt[p2] - used[p2] > rem) { rem = b.cnt[p2] - used[p2]; best = p2; }
+                if (best >= 0) { sl[q] = b.slot[best][used[best]++]; live[q] = true; }
+                else sl[q] = (unsigned short)(q < nneed ? q : any);      // padding: a staged slot, all-zero block column
+            }
             unsigned mask = 0;
             const int first = base;
             for (int lr = 0; lr < 8; ++lr) {
                 const int r = row0 + lr;
                 if (r >= row1) break;
                 for (int q = 0; q < 4; ++q) {
-                    if (t >= b.cnt[q]) continue;
+                    if (!live[q]) continue;
                     double sum = 0.0;
                     bool has = false;
                     for (int w = 0; w < W; ++w)
