@@ -188,94 +188,126 @@ __device__ bool td_bins(const unsigned short* __restrict__ ec, const double* __r
     return true;
 }
 
-// stats[0] = max k-tiles per chunk, stats[1] = max nonzeros per chunk, stats[2] = not representable, stats[3] = max k-tiles per row group
-__global__ void tile_dmma_count_kernel(int nchunks, int dl, int e8, const int* __restrict__ desc, const unsigned short* __restrict__ ecol,
-                                       const double* __restrict__ eval, int* __restrict__ stats) {
-    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cidx >= nchunks) return;
-    const int* dsc = desc + (size_t)cidx * dl;
-    const int nr = dsc[1], W = dsc[3];
-    const unsigned short* ec = ecol + (size_t)cidx * e8;
-    const double* ev = eval + (size_t)cidx * e8;
-    if (nr > 32) { stats[2] = 1; return; }
-    TdBins b;
-    int tiles = 0, nz = 0;
-    for (int g = 0; g < 4; ++g) {
-        const int row0 = g * 8, row1 = min(row0 + 8, nr);
-        if (row0 >= row1) break;
-        if (!td_bins(ec, ev, W, row0, row1, b)) { stats[2] = 1; return; }
-        const int kt = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
-        tiles += kt;
-        atomicMax(&stats[3], kt);
-        for (int t = row0 * W; t < row1 * W; ++t) nz += (ev[t] != 0.0);
+constexpr int TD_MAXKT = 16;      // k-tiles per row group the builder can form (the kernel keeps DM_KTR of them in registers)
+
+// k-tiles of one row group from its bins (see above); live[t] bit q: position q of tile t carries a slot of the group
+__device__ int td_form(const TdBins& b, int nneed, unsigned short (*sl)[4], unsigned char* live) {
+    const int KT = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
+    int used[4] = {0, 0, 0, 0};
+    unsigned short any = 0;
+    for (int q = 0; q < 4; ++q)
+        if (b.cnt[q]) any = b.slot[q][0];
+    for (int t = 0; t < KT && t < TD_MAXKT; ++t) {
+        unsigned lv = 0;
+        for (int q = 0; q < 4; ++q)
+            if (used[q] < b.cnt[q]) { sl[t][q] = b.slot[q][used[q]++]; lv |= 1u << q; }
+        for (int q = 0; q < 4; ++q) {
+            if (lv & (1u << q)) continue;
+            int best = -1, rem = 0;
+            for (int p2 = 0; p2 < 4; ++p2)
+                if (b.cnt[p2] - used[p2] > rem) { rem = b.cnt[p2] - used[p2]; best = p2; }
+            if (best >= 0) { sl[t][q] = b.slot[best][used[best]++]; lv |= 1u << q; }
+            else sl[t][q] = (unsigned short)(q < nneed ? q : any);      // padding: a staged slot, all-zero block column
+        }
+        live[t] = (unsigned char)lv;
     }
-    atomicMax(&stats[0], tiles);
-    atomicMax(&stats[1], nz);
+    return KT;
 }
 
-// write_meta: also fills the k-tile records and desc[6]; pat decides which entries exist, src supplies their values
+// One thread per (chunk, row group).  rgcnt[chunk][group] = (k-tiles, nonzero entries);
+// stats[0] = max k-tiles per chunk, stats[1] = max nonzeros per chunk, stats[2] = not representable, stats[3] = max k-tiles per row group
+__global__ void tile_dmma_count_kernel(int nchunks, int dl, int e8, const int* __restrict__ desc, const unsigned short* __restrict__ ecol,
+                                       const double* __restrict__ eval, ushort2* __restrict__ rgcnt, int* __restrict__ stats) {
+    const int tidg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cidx = tidg >> 2, g = tidg & 3;
+    int kt = 0, nz = 0;
+    if (cidx < nchunks) {
+        const int* dsc = desc + (size_t)cidx * dl;
+        const int nr = dsc[1], nneed = dsc[2], W = dsc[3];
+        const unsigned short* ec = ecol + (size_t)cidx * e8;
+        const double* ev = eval + (size_t)cidx * e8;
+        if (nr > 32 || nneed > 64) stats[2] = 1;
+        const int row0 = g * 8, row1 = min(row0 + 8, nr);
+        if (row0 < row1 && nr <= 32 && nneed <= 64) {
+            TdBins b;
+            if (!td_bins(ec, ev, W, row0, row1, b)) stats[2] = 1;
+            else {
+                kt = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
+                if (kt > TD_MAXKT) stats[2] = 1;
+                for (int t = row0 * W; t < row1 * W; ++t) nz += (ev[t] != 0.0);
+            }
+        }
+        rgcnt[tidg] = make_ushort2((unsigned short)kt, (unsigned short)nz);
+        atomicMax(&stats[3], kt);
+    }
+    // chunk totals over the four threads of a chunk (adjacent lanes)
+    int tk = kt, tn = nz;
+    tk += __shfl_xor_sync(0xffffffffu, tk, 1); tn += __shfl_xor_sync(0xffffffffu, tn, 1);
+    tk += __shfl_xor_sync(0xffffffffu, tk, 2); tn += __shfl_xor_sync(0xffffffffu, tn, 2);
+    if (cidx < nchunks && g == 0) {
+        atomicMax(&stats[0], tk);
+        atomicMax(&stats[1], tn);
+    }
+}
+
+// write_meta: also fills the k-tile records and desc[6]; pat decides which entries exist, src supplies their values.
+// apack must be zero on entry (entries are accumulated, so repeated columns of a row add up).
 __global__ void tile_dmma_fill_kernel(int nchunks, int dl, int e8, int kts, int ap8, int write_meta, int* __restrict__ desc,
                                       const unsigned short* __restrict__ ecol, const double* __restrict__ pat,
-                                      const double* __restrict__ src, uint4* __restrict__ ktmeta, double* __restrict__ apack) {
-    const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+                                      const double* __restrict__ src, const ushort2* __restrict__ rgcnt, uint4* __restrict__ ktmeta,
+                                      double* __restrict__ apack) {
+    const int tidg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cidx = tidg >> 2, g = tidg & 3;
     if (cidx >= nchunks) return;
     int* dsc = desc + (size_t)cidx * dl;
     const int nr = dsc[1], nneed = dsc[2], W = dsc[3];
     const unsigned short* ec = ecol + (size_t)cidx * e8;
     const double* pt = pat + (size_t)cidx * e8;
     const double* sv = src + (size_t)cidx * e8;
-    uint4* meta = ktmeta + (size_t)cidx * kts;
-    double* ap = apack + (size_t)cidx * ap8;
-    TdBins b;
-    int tile = 0, base = 0;
+    int tile0 = 0, base0 = 0;
     unsigned counts = 0;
-    for (int g = 0; g < 4; ++g) {
-        const int row0 = g * 8, row1 = min(row0 + 8, nr);
-        if (row0 >= row1) break;
-        td_bins(ec, pt, W, row0, row1, b);
-        const int KT = (b.cnt[0] + b.cnt[1] + b.cnt[2] + b.cnt[3] + 3) >> 2;
-        counts |= (unsigned)KT << (8 * g);
-        int used[4] = {0, 0, 0, 0};
-        unsigned short any = 0;
-        for (int q = 0; q < 4; ++q)
-            if (b.cnt[q]) any = b.slot[q][0];
-        for (int t = 0; t < KT; ++t) {
-            unsigned short sl[4];
-            bool live[4];
-            for (int q = 0; q < 4; ++q) {
-                live[q] = used[q] < b.cnt[q];
-                if (live[q]) sl[q] = b.slot[q][used[q]++];
-            }
-            for (int q = 0; q < 4; ++q) {
-                if (live[q]) continue;
-                int best = -1, rem = 0;
-                for (int p2 = 0; p2 < 4; ++p2)
-                    if (b.cnt[p2] - used[p2] > rem) { rem = b.cnt[p2] - used[p2]; best = p2; }
-                if (best >= 0) { sl[q] = b.slot[best][used[best]++]; live[q] = true; }
-                else sl[q] = (unsigned short)(q < nneed ? q : any);      // padding: a staged slot, all-zero block column
-            }
-            unsigned mask = 0;
-            const int first = base;
-            for (int lr = 0; lr < 8; ++lr) {
-                const int r = row0 + lr;
-                if (r >= row1) break;
-                for (int q = 0; q < 4; ++q) {
-                    if (!live[q]) continue;
-                    double sum = 0.0;
-                    bool has = false;
-                    for (int w = 0; w < W; ++w)
-                        if (pt[r * W + w] != 0.0 && ec[r * W + w] == sl[q]) { sum += sv[r * W + w]; has = true; }
-                    if (has) {
-                        mask |= 1u << (lr * 4 + q);
-                        ap[base++] = sum;
-                    }
-                }
-            }
-            if (write_meta) meta[tile] = make_uint4((unsigned)sl[0] | ((unsigned)sl[1] << 16), (unsigned)sl[2] | ((unsigned)sl[3] << 16), mask, (unsigned)first);
-            ++tile;
-        }
+    for (int g2 = 0; g2 < 4; ++g2) {
+        const ushort2 cn = rgcnt[cidx * 4 + g2];
+        counts |= (unsigned)cn.x << (8 * g2);
+        if (g2 < g) { tile0 += cn.x; base0 += cn.y; }
     }
-    if (write_meta) dsc[6] = (int)counts;
+    if (write_meta && g == 0) dsc[6] = (int)counts;
+    const int row0 = g * 8, row1 = min(row0 + 8, nr);
+    if (row0 >= row1) return;
+    TdBins b;
+    td_bins(ec, pt, W, row0, row1, b);
+    unsigned short sl[TD_MAXKT][4];
+    unsigned char live[TD_MAXKT];
+    const int KT = td_form(b, nneed, sl, live);
+    unsigned char where[64];
+    for (int i = 0; i < 64; ++i) where[i] = 0xff;
+    for (int t = 0; t < KT; ++t)
+        for (int q = 0; q < 4; ++q)
+            if (live[t] & (1u << q)) where[sl[t][q]] = (unsigned char)(t * 4 + q);
+    unsigned mask[TD_MAXKT];
+    for (int t = 0; t < KT; ++t) mask[t] = 0;
+    for (int r = row0; r < row1; ++r)
+        for (int w = 0; w < W; ++w)
+            if (pt[r * W + w] != 0.0) {
+                const int pos = where[ec[r * W + w]];
+                mask[pos >> 2] |= 1u << ((r - row0) * 4 + (pos & 3));
+            }
+    int first[TD_MAXKT];
+    int acc = base0;
+    for (int t = 0; t < KT; ++t) { first[t] = acc; acc += __popc(mask[t]); }
+    double* ap = apack + (size_t)cidx * ap8;
+    for (int r = row0; r < row1; ++r)
+        for (int w = 0; w < W; ++w)
+            if (pt[r * W + w] != 0.0) {
+                const int pos = where[ec[r * W + w]];
+                const int t = pos >> 2, bit = (r - row0) * 4 + (pos & 3);
+                ap[first[t] + __popc(mask[t] & ((1u << bit) - 1u))] += sv[r * W + w];
+            }
+    if (write_meta) {
+        uint4* meta = ktmeta + (size_t)cidx * kts + tile0;
+        for (int t = 0; t < KT; ++t)
+            meta[t] = make_uint4((unsigned)sl[t][0] | ((unsigned)sl[t][1] << 16), (unsigned)sl[t][2] | ((unsigned)sl[t][3] << 16), mask[t], (unsigned)first[t]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ apply
@@ -317,7 +349,7 @@ __device__ __forceinline__ void cp8(void* smem_dst, const void* __restrict__ src
 // stage (more resident CTAs) and two fewer shared-memory passes per row.
 template <int CW, int VEC, int MODE, bool BREG>
 __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(TileDev op, TileArgs a) {
-    extern __shared__ __align__(16) unsigned char sm[];
+    extern __shared__ __align__(128) unsigned char sm[];
     constexpr int SW = CW * VEC;
     constexpr int SWB = SW * 8;
     constexpr int RPW = 32 / CW;
@@ -1031,7 +1063,7 @@ int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs&
 
 void tileop_free(TileOp* op) {
     if (!op) return;
-    void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled, op->ktmeta, op->apack, op->apack_scaled};
+    void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled, op->ktmeta, op->apack, op->apack_scaled, op->rgcnt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *op = TileOp();
@@ -1044,10 +1076,11 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     int* stats = nullptr;
     CUDA_TRY(c, cudaMalloc(&stats, sizeof(int) * 4));
     CUDA_TRY(c, cudaMemsetAsync(stats, 0, sizeof(int) * 4, c->stream));
-    const int tb = 64, nb = (op->nchunks + tb - 1) / tb;
+    const int tb = 128, nb = (4 * op->nchunks + tb - 1) / tb;      // one thread per (chunk, row group)
+    CUDA_TRY(c, cudaMalloc(&op->rgcnt, sizeof(ushort2) * 4 * (size_t)op->nchunks));
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
-        tile_dmma_count_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->desc, op->ecol, op->eval, stats);
+        tile_dmma_count_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->desc, op->ecol, op->eval, op->rgcnt, stats);
         c->launches++;
     }
     int h[4] = {0, 0, 0, 0};
@@ -1065,7 +1098,7 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
         tile_dmma_fill_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, kts, ap8, 1, op->desc, op->ecol, op->eval, op->eval,
-                                                        op->ktmeta, op->apack);
+                                                        op->rgcnt, op->ktmeta, op->apack);
         KCHECK(c);
     }
     op->kts = kts; op->ap8 = ap8;
@@ -1137,8 +1170,9 @@ int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv) {
         size_t nc = (size_t)op->nchunks;
         if (!op->apack_scaled) CUDA_TRY(c, cudaMalloc(&op->apack_scaled, sizeof(double) * nc * op->ap8));
         CUDA_TRY(c, cudaMemsetAsync(op->apack_scaled, 0, sizeof(double) * nc * op->ap8, c->stream));
-        tile_dmma_fill_kernel<<<(op->nchunks + 63) / 64, 64, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->kts, op->ap8, 0, op->desc, op->ecol,
-                                                                            op->eval, op->eval_scaled, op->ktmeta, op->apack_scaled);
+        tile_dmma_fill_kernel<<<(4 * op->nchunks + 127) / 128, 128, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->kts, op->ap8, 0, op->desc,
+                                                                                   op->ecol, op->eval, op->eval_scaled, op->rgcnt, op->ktmeta,
+                                                                                   op->apack_scaled);
         KCHECK(c);
     }
     return SFEM_OK;

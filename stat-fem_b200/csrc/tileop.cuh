@@ -40,6 +40,7 @@ struct TileOp {
     uint4* ktmeta = nullptr;          // [nchunks][kts] {slot0 | slot1 << 16, slot2 | slot3 << 16, lane mask, first value}
     double* apack = nullptr;          // [nchunks][ap8]
     double* apack_scaled = nullptr;   // [nchunks][ap8] from eval_scaled
+    ushort2* rgcnt = nullptr;         // [nchunks][4] (k-tiles, nonzeros) of every row group (builder bookkeeping)
 };
 
 enum {
