@@ -51,9 +51,12 @@ int dense_posterior_cov(sfem_ctx* c, int n, int d, const double* Xs, const doubl
 int dense_solve_shifted(sfem_ctx* c, int n, int d, const double* Xs, const double* unc, int unc_vec, double sigma, double l,
                         double rho2, const double* Cu, const double* b, double* x, void* work, size_t work_bytes);
 
+thread_local cudaStream_t sfem_tls_stream = nullptr;
+
 #define GUARD(ctx)                   \
     if (!(ctx)) return SFEM_ERR_ARG; \
-    cudaSetDevice((ctx)->device);
+    cudaSetDevice((ctx)->device);    \
+    sfem_tls_stream = (ctx)->stream;
 
 extern "C" {
 
@@ -72,6 +75,13 @@ int sfem_create(sfem_ctx** out, int device, void* cuda_stream) {
     sfem_ctx* c = new sfem_ctx();
     c->device = device;
     c->stream = (cudaStream_t)cuda_stream;
+    {   // keep freed blocks in the pool (see sfem_dev_malloc in common.cuh)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (const char* e = getenv("SFEM_TILE_ROWS")) c->tile_rows = atoi(e);     // tuning knobs of the staged-tile kernels
     if (const char* e = getenv("SFEM_TILE_SW")) c->tile_sw = atoi(e);
     if (const char* e = getenv("SFEM_TILE_DMMA")) c->tile_dmma = atoi(e);
@@ -86,13 +96,14 @@ int sfem_create(sfem_ctx** out, int device, void* cuda_stream) {
 int sfem_destroy(sfem_ctx* c) {
     if (!c) return SFEM_OK;
     cudaSetDevice(c->device);
+    sfem_tls_stream = c->stream;
     cudaStreamSynchronize(c->stream);
     mg_free(c);
     gcov_free(c);
     prof_free(c);
-    if (c->A_dinv) cudaFree(c->A_dinv);
-    if (c->scratch) cudaFree(c->scratch);
-    if (c->dense_tmp) cudaFree(c->dense_tmp);
+    if (c->A_dinv) sfem_dev_free(c->A_dinv);
+    if (c->scratch) sfem_dev_free(c->scratch);
+    if (c->dense_tmp) sfem_dev_free(c->dense_tmp);
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_aux) cudaEventDestroy(c->ev_aux);

@@ -268,11 +268,11 @@ static void* dense_tmp(sfem_ctx* c, size_t bytes) {
     if (bytes <= c->dense_tmp_bytes && c->dense_tmp) return c->dense_tmp;
     if (c->dense_tmp) {
         cudaStreamSynchronize(c->stream);
-        cudaFree(c->dense_tmp);
+        sfem_dev_free(c->dense_tmp);
         c->dense_tmp = nullptr;
         c->dense_tmp_bytes = 0;
     }
-    if (cudaMalloc(&c->dense_tmp, bytes + 4096) != cudaSuccess) {
+    if (sfem_dev_malloc(&c->dense_tmp, bytes + 4096) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }

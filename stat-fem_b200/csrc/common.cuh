@@ -77,6 +77,17 @@ struct sfem_ctx {
 };
 
 int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);
+
+// Device memory of the library (multigrid hierarchy, operator records, temporaries) is stream-ordered: allocated and
+// freed with cudaMallocAsync / cudaFreeAsync on the stream of the context that is executing (set by every entry point
+// of capi.cu), from the device's default pool with an unlimited release threshold.  Tearing down a hierarchy of a few
+// GB therefore costs microseconds instead of ~100 synchronising cudaFree calls (0.2 s per solver at 1M DOF).
+extern thread_local cudaStream_t sfem_tls_stream;
+template <typename T>
+inline cudaError_t sfem_dev_malloc(T** p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), bytes > 0 ? bytes : 16, sfem_tls_stream);
+}
+inline cudaError_t sfem_dev_free(void* p) { return p ? cudaFreeAsync(p, sfem_tls_stream) : cudaSuccess; }
 void* sfem_scratch(sfem_ctx* c, size_t bytes);   // returns device scratch of at least `bytes` (may realloc)
 
 #define CUDA_TRY(c, expr)                                                                         \

@@ -280,8 +280,8 @@ GcP make_params(const sfem_ctx* c) {
 }  // namespace
 
 void gcov_free(sfem_ctx* c) {
-    if (c->gc.cell_start) cudaFree(c->gc.cell_start);
-    if (c->gc.cell_nodes) cudaFree(c->gc.cell_nodes);
+    if (c->gc.cell_start) sfem_dev_free(c->gc.cell_start);
+    if (c->gc.cell_nodes) sfem_dev_free(c->gc.cell_nodes);
     c->gc.cell_start = nullptr;
     c->gc.cell_nodes = nullptr;
 }
@@ -330,14 +330,14 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
     if (!s) return sfem_fail(c, SFEM_ERR_CUDA, "gcov_count: scratch allocation failed");
     // the cell-list builder also uses the scratch arena, so cell_of lives in its own allocation
     int* cell_of = nullptr;
-    CUDA_TRY(c, cudaMalloc(&cell_of, sizeof(int) * (size_t)n));
+    CUDA_TRY(c, sfem_dev_malloc(&cell_of, sizeof(int) * (size_t)n));
     GcP p = make_params(c);
     cell_of_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(p, cell_of);
     KCHECK(c);
     int rc = build_cell_list(c, cell_of, n, g.ncell, &g.cell_start, &g.cell_nodes);
-    if (rc) { cudaFree(cell_of); return rc; }
+    if (rc) { sfem_dev_free(cell_of); return rc; }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(cell_of);
+    sfem_dev_free(cell_of);
 
     s = (unsigned char*)sfem_scratch(c, bytes);
     if (!s) return sfem_fail(c, SFEM_ERR_CUDA, "gcov_count: scratch allocation failed");

@@ -278,22 +278,22 @@ int mg_build_tiles(sfem_ctx* c);
 void mg_free(sfem_ctx* c) {
     for (MGLevel* L : c->mg) {
         mg_tiles_free(L);
-        if (L->stencil) cudaFree(L->stencil);
-        if (L->dinv) cudaFree(L->dinv);
-        if (L->constrained) cudaFree(L->constrained);
-        if (L->cidx) cudaFree(L->cidx);
-        if (L->frac) cudaFree(L->frac);
-        if (L->cell_start) cudaFree(L->cell_start);
-        if (L->cell_nodes) cudaFree(L->cell_nodes);
-        if (L->dense_inv) cudaFree(L->dense_inv);
+        if (L->stencil) sfem_dev_free(L->stencil);
+        if (L->dinv) sfem_dev_free(L->dinv);
+        if (L->constrained) sfem_dev_free(L->constrained);
+        if (L->cidx) sfem_dev_free(L->cidx);
+        if (L->frac) sfem_dev_free(L->frac);
+        if (L->cell_start) sfem_dev_free(L->cell_start);
+        if (L->cell_nodes) sfem_dev_free(L->cell_nodes);
+        if (L->dense_inv) sfem_dev_free(L->dense_inv);
         delete L;
     }
     c->mg.clear();
 }
 
 int stiffness_dinv(sfem_ctx* c) {
-    if (c->A_dinv) cudaFree(c->A_dinv);
-    CUDA_TRY(c, cudaMalloc(&c->A_dinv, sizeof(double) * (size_t)c->n));
+    if (c->A_dinv) sfem_dev_free(c->A_dinv);
+    CUDA_TRY(c, sfem_dev_malloc(&c->A_dinv, sizeof(double) * (size_t)c->n));
     csr_dinv_kernel<<<(unsigned)cdiv64(c->n, 256), 256, 0, c->stream>>>(c->n, c->A_ptr, c->A_idx, c->A_val, c->A_dinv);
     KCHECK(c);
     return SFEM_OK;
@@ -311,13 +311,13 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
     MGLevel* L0 = new MGLevel();
     c->mg.push_back(L0);
     L0->kind = 0; L0->n = n; L0->d = dim;
-    CUDA_TRY(c, cudaMalloc(&L0->constrained, (size_t)n));
+    CUDA_TRY(c, sfem_dev_malloc(&L0->constrained, (size_t)n));
     CUDA_TRY(c, cudaMemcpyAsync(L0->constrained, bc_mask, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_TRY(c, cudaMalloc(&L0->dinv, sizeof(double) * (size_t)n));
+    CUDA_TRY(c, sfem_dev_malloc(&L0->dinv, sizeof(double) * (size_t)n));
     fine_wdinv_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(n, omega, c->A_dinv, L0->constrained, L0->dinv);
     KCHECK(c);
-    CUDA_TRY(c, cudaMalloc(&L0->cidx, sizeof(int) * (size_t)n));
-    CUDA_TRY(c, cudaMalloc(&L0->frac, sizeof(double) * (size_t)n * dim));
+    CUDA_TRY(c, sfem_dev_malloc(&L0->cidx, sizeof(int) * (size_t)n));
+    CUDA_TRY(c, sfem_dev_malloc(&L0->frac, sizeof(double) * (size_t)n * dim));
     // ---- level 1 lattice
     MGLevel* L1 = new MGLevel();
     c->mg.push_back(L1);
@@ -339,9 +339,9 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
     KCHECK(c);
     int rc = build_cell_list(c, L0->cidx, n, (int)ncell, &L0->cell_start, &L0->cell_nodes);
     if (rc) return rc;
-    CUDA_TRY(c, cudaMalloc(&L1->constrained, (size_t)lat1.n));
-    CUDA_TRY(c, cudaMalloc(&L1->stencil, sizeof(double) * (size_t)lat1.n * lat1.S));
-    CUDA_TRY(c, cudaMalloc(&L1->dinv, sizeof(double) * (size_t)lat1.n));
+    CUDA_TRY(c, sfem_dev_malloc(&L1->constrained, (size_t)lat1.n));
+    CUDA_TRY(c, sfem_dev_malloc(&L1->stencil, sizeof(double) * (size_t)lat1.n * lat1.S));
+    CUDA_TRY(c, sfem_dev_malloc(&L1->dinv, sizeof(double) * (size_t)lat1.n));
     l1_constrained_kernel<<<(unsigned)cdiv64(lat1.n, 4), 128, 0, c->stream>>>(lat1, dim, L0->cell_start, L0->cell_nodes,
                                                                              L0->frac, L0->constrained, L1->constrained);
     KCHECK(c);
@@ -383,9 +383,9 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
         c->mg.push_back(C);
         Lat lc = make_lat(dim, C->m);
         C->n = lc.n; C->S = lc.S;
-        CUDA_TRY(c, cudaMalloc(&C->constrained, (size_t)lc.n));
-        CUDA_TRY(c, cudaMalloc(&C->stencil, sizeof(double) * (size_t)lc.n * lc.S));
-        CUDA_TRY(c, cudaMalloc(&C->dinv, sizeof(double) * (size_t)lc.n));
+        CUDA_TRY(c, sfem_dev_malloc(&C->constrained, (size_t)lc.n));
+        CUDA_TRY(c, sfem_dev_malloc(&C->stencil, sizeof(double) * (size_t)lc.n * lc.S));
+        CUDA_TRY(c, sfem_dev_malloc(&C->dinv, sizeof(double) * (size_t)lc.n));
         LatPair P = make_pair(F, C);
         lat_constrained_kernel<<<(unsigned)cdiv64(lc.n, 256), 256, 0, c->stream>>>(P, F->constrained, C->constrained);
         KCHECK(c);
@@ -399,7 +399,7 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
     if (F->n <= 1200) {
         Lat lc = make_lat(dim, F->m);
         int nn = (int)lc.n;
-        CUDA_TRY(c, cudaMalloc(&F->dense_inv, sizeof(double) * (size_t)nn * nn));
+        CUDA_TRY(c, sfem_dev_malloc(&F->dense_inv, sizeof(double) * (size_t)nn * nn));
         CUDA_TRY(c, cudaMemsetAsync(F->dense_inv, 0, sizeof(double) * (size_t)nn * nn, c->stream));
         lat_to_dense_kernel<<<(unsigned)cdiv64(lc.n * lc.S, 256), 256, 0, c->stream>>>(lc, dim, F->stencil, F->dense_inv);
         KCHECK(c);

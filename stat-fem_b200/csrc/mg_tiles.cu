@@ -264,9 +264,9 @@ __global__ void gen_fill_kernel(Gen g, int64_t nrows, const int64_t* __restrict_
 template <class Gen>
 int build_op(sfem_ctx* c, const Gen& g, int64_t nrows, int64_t ncols, const int* chunk_ptr, int nchunks, int max_rows, TileOp* out) {
     int64_t *counts = nullptr, *ptr = nullptr, *sums = nullptr;
-    CUDA_TRY(c, cudaMalloc(&counts, sizeof(int64_t) * (size_t)(nrows + 1)));
-    CUDA_TRY(c, cudaMalloc(&ptr, sizeof(int64_t) * (size_t)(nrows + 1)));
-    CUDA_TRY(c, cudaMalloc(&sums, sizeof(int64_t) * (size_t)(nrows / 1024 + 8)));
+    CUDA_TRY(c, sfem_dev_malloc(&counts, sizeof(int64_t) * (size_t)(nrows + 1)));
+    CUDA_TRY(c, sfem_dev_malloc(&ptr, sizeof(int64_t) * (size_t)(nrows + 1)));
+    CUDA_TRY(c, sfem_dev_malloc(&sums, sizeof(int64_t) * (size_t)(nrows / 1024 + 8)));
     int rc;
     int32_t* idx = nullptr;
     double* val = nullptr;
@@ -281,8 +281,8 @@ int build_op(sfem_ctx* c, const Gen& g, int64_t nrows, int64_t ncols, const int*
         cudaMemcpyAsync(&nnz, ptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: operator count failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    if (rc == SFEM_OK && (cudaMalloc(&idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess ||
-                          cudaMalloc(&val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess))
+    if (rc == SFEM_OK && (sfem_dev_malloc(&idx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess ||
+                          sfem_dev_malloc(&val, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess))
         rc = sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: out of memory");
     if (rc == SFEM_OK) {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
@@ -291,9 +291,9 @@ int build_op(sfem_ctx* c, const Gen& g, int64_t nrows, int64_t ncols, const int*
         rc = tileop_build(c, nrows, ncols, ptr, idx, val, chunk_ptr, nchunks, max_rows, out);
     }
     cudaStreamSynchronize(c->stream);
-    cudaFree(counts); cudaFree(ptr); cudaFree(sums);
-    if (idx) cudaFree(idx);
-    if (val) cudaFree(val);
+    sfem_dev_free(counts); sfem_dev_free(ptr); sfem_dev_free(sums);
+    if (idx) sfem_dev_free(idx);
+    if (val) sfem_dev_free(val);
     return rc;
 }
 
@@ -322,10 +322,10 @@ __global__ void coarse_dense_kernel(int n, int k, const double* __restrict__ Ain
 }  // namespace
 
 void mg_tiles_free(MGLevel* L) {
-    if (L->perm) cudaFree(L->perm);
-    if (L->iperm) cudaFree(L->iperm);
-    if (L->dinv_t) cudaFree(L->dinv_t);
-    if (L->dinv_t2) cudaFree(L->dinv_t2);
+    if (L->perm) sfem_dev_free(L->perm);
+    if (L->iperm) sfem_dev_free(L->iperm);
+    if (L->dinv_t) sfem_dev_free(L->dinv_t);
+    if (L->dinv_t2) sfem_dev_free(L->dinv_t2);
     L->dinv_t2 = nullptr;
     L->perm = L->iperm = nullptr;
     L->dinv_t = nullptr;
@@ -344,7 +344,7 @@ int mg_build_tiles(sfem_ctx* c) {
     std::vector<int*> chunk_ptr(nl, nullptr);
     std::vector<int> nchunks(nl, 0), max_rows(nl, 0);
     int rc = SFEM_OK;
-    auto cleanup = [&]() { for (int* p : chunk_ptr) if (p) cudaFree(p); };
+    auto cleanup = [&]() { for (int* p : chunk_ptr) if (p) sfem_dev_free(p); };
 #define TRY_RC(expr) do { rc = (expr); if (rc) { cleanup(); return rc; } } while (0)
 #define TRY_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return sfem_fail(c, SFEM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); } } while (0)
 
@@ -363,22 +363,22 @@ int mg_build_tiles(sfem_ctx* c) {
         }
         if (total_bits > 26) return sfem_fail(c, SFEM_ERR_LIMIT, "mg tiles: level-1 lattice too fine for the Morton cell list");
         int* key = nullptr;
-        TRY_CUDA(cudaMalloc(&key, sizeof(int) * (size_t)n));
+        TRY_CUDA(sfem_dev_malloc(&key, sizeof(int) * (size_t)n));
         morton_key_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(n, M, L0->cidx, key);
         c->launches++;
         int* start = nullptr;
         rc = build_cell_list(c, key, n, 1 << total_bits, &start, &L0->perm);
         cudaStreamSynchronize(c->stream);
-        cudaFree(key);
-        if (start) cudaFree(start);
+        sfem_dev_free(key);
+        if (start) sfem_dev_free(start);
         if (rc) { cleanup(); return rc; }
-        TRY_CUDA(cudaMalloc(&L0->iperm, sizeof(int) * (size_t)n));
+        TRY_CUDA(sfem_dev_malloc(&L0->iperm, sizeof(int) * (size_t)n));
         invert_perm_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>(n, L0->perm, L0->iperm);
         c->launches++;
         const int R0 = c->tile_rows > 0 ? c->tile_rows : 32;
         nchunks[0] = (int)cdiv64(n, R0);
         max_rows[0] = R0;
-        TRY_CUDA(cudaMalloc(&chunk_ptr[0], sizeof(int) * ((size_t)nchunks[0] + 1)));
+        TRY_CUDA(sfem_dev_malloc(&chunk_ptr[0], sizeof(int) * ((size_t)nchunks[0] + 1)));
         uniform_chunks_kernel<<<(nchunks[0] + 256) / 256, 256, 0, c->stream>>>(nchunks[0], R0, n, chunk_ptr[0]);
         c->launches++;
     }
@@ -390,29 +390,29 @@ int mg_build_tiles(sfem_ctx* c) {
             const int R = 128;
             nchunks[l] = (int)cdiv64(L->n, R);
             max_rows[l] = R;
-            TRY_CUDA(cudaMalloc(&chunk_ptr[l], sizeof(int) * ((size_t)nchunks[l] + 1)));
+            TRY_CUDA(sfem_dev_malloc(&chunk_ptr[l], sizeof(int) * ((size_t)nchunks[l] + 1)));
             uniform_chunks_kernel<<<(nchunks[l] + 256) / 256, 256, 0, c->stream>>>(nchunks[l], R, L->n, chunk_ptr[l]);
             c->launches++;
             continue;      // identity numbering
         }
         TileGeom g = make_geom(L);
-        TRY_CUDA(cudaMalloc(&L->perm, sizeof(int) * (size_t)L->n));
-        TRY_CUDA(cudaMalloc(&L->iperm, sizeof(int) * (size_t)L->n));
+        TRY_CUDA(sfem_dev_malloc(&L->perm, sizeof(int) * (size_t)L->n));
+        TRY_CUDA(sfem_dev_malloc(&L->iperm, sizeof(int) * (size_t)L->n));
         lat_perm_kernel<<<(unsigned)cdiv64(L->n, 256), 256, 0, c->stream>>>(g, L->n, L->perm, L->iperm);
         c->launches++;
         nchunks[l] = g.nt[0] * g.nt[1] * g.nt[2];
         max_rows[l] = imin(g.T[0], g.m[0]) * imin(g.T[1], g.m[1]) * imin(g.T[2], g.m[2]);
-        TRY_CUDA(cudaMalloc(&chunk_ptr[l], sizeof(int) * ((size_t)nchunks[l] + 1)));
+        TRY_CUDA(sfem_dev_malloc(&chunk_ptr[l], sizeof(int) * ((size_t)nchunks[l] + 1)));
         lat_chunk_kernel<<<(nchunks[l] + 256) / 256, 256, 0, c->stream>>>(g, nchunks[l], L->n, chunk_ptr[l]);
         c->launches++;
     }
     // ---- smoother scalings in the new numbering
     for (int l = 0; l < nl; ++l) {
         MGLevel* L = c->mg[l];
-        TRY_CUDA(cudaMalloc(&L->dinv_t, sizeof(double) * (size_t)L->n));
+        TRY_CUDA(sfem_dev_malloc(&L->dinv_t, sizeof(double) * (size_t)L->n));
         permute_vector_kernel<<<(unsigned)cdiv64(L->n, 256), 256, 0, c->stream>>>(L->n, L->perm, L->dinv, L->dinv_t);
         c->launches++;
-        TRY_CUDA(cudaMalloc(&L->dinv_t2, sizeof(double) * (size_t)L->n));
+        TRY_CUDA(sfem_dev_malloc(&L->dinv_t2, sizeof(double) * (size_t)L->n));
         second_weight_kernel<<<(unsigned)cdiv64(L->n, 256), 256, 0, c->stream>>>(L->n, L->perm, L->dinv, L->constrained,
                                                                                c->mg_omega2 / c->mg_omega, L->dinv_t2);
         c->launches++;
@@ -425,12 +425,12 @@ int mg_build_tiles(sfem_ctx* c) {
         if (parts <= 1) return build_op(c, gen, nrows, ncols, chunk_ptr[l_rows], nchunks[l_rows], max_rows[l_rows], out);
         int* fine = nullptr;
         int nf = nchunks[l_rows] * parts;
-        if (cudaMalloc(&fine, sizeof(int) * ((size_t)nf + 1)) != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: out of memory");
+        if (sfem_dev_malloc(&fine, sizeof(int) * ((size_t)nf + 1)) != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: out of memory");
         refine_chunks_kernel<<<(nf + 256) / 256, 256, 0, c->stream>>>(nchunks[l_rows], sub, parts, chunk_ptr[l_rows], fine);
         c->launches++;
         int r = build_op(c, gen, nrows, ncols, fine, nf, sub, out);
         cudaStreamSynchronize(c->stream);
-        cudaFree(fine);
+        sfem_dev_free(fine);
         return r;
     };
     // ---- operators

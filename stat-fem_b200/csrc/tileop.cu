@@ -1065,7 +1065,7 @@ void tileop_free(TileOp* op) {
     if (!op) return;
     void* ptrs[] = {op->desc, op->need, op->ecol, op->eval, op->eval_scaled, op->ktmeta, op->apack, op->apack_scaled, op->rgcnt};
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        if (p) sfem_dev_free(p);
     *op = TileOp();
 }
 
@@ -1074,10 +1074,10 @@ void tileop_free(TileOp* op) {
 static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     if (op->nchunks <= 0) return SFEM_OK;
     int* stats = nullptr;
-    CUDA_TRY(c, cudaMalloc(&stats, sizeof(int) * 4));
+    CUDA_TRY(c, sfem_dev_malloc(&stats, sizeof(int) * 4));
     CUDA_TRY(c, cudaMemsetAsync(stats, 0, sizeof(int) * 4, c->stream));
     const int tb = 128, nb = (4 * op->nchunks + tb - 1) / tb;      // one thread per (chunk, row group)
-    CUDA_TRY(c, cudaMalloc(&op->rgcnt, sizeof(ushort2) * 4 * (size_t)op->nchunks));
+    CUDA_TRY(c, sfem_dev_malloc(&op->rgcnt, sizeof(ushort2) * 4 * (size_t)op->nchunks));
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
         tile_dmma_count_kernel<<<nb, tb, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->desc, op->ecol, op->eval, op->rgcnt, stats);
@@ -1086,13 +1086,13 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     int h[4] = {0, 0, 0, 0};
     cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(stats);
+    sfem_dev_free(stats);
     if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: k-tile count failed: %s", cudaGetErrorString(e));
     if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DM_KTR || op->max_need > 64) return SFEM_OK;      // the kernel keeps a row group's k-tiles in registers
     const int kts = h[0], ap8 = h[1] > 0 ? (h[1] + 1) & ~1 : 2;
     size_t nc = (size_t)op->nchunks;
-    CUDA_TRY(c, cudaMalloc(&op->ktmeta, sizeof(uint4) * nc * kts));
-    CUDA_TRY(c, cudaMalloc(&op->apack, sizeof(double) * nc * ap8));
+    CUDA_TRY(c, sfem_dev_malloc(&op->ktmeta, sizeof(uint4) * nc * kts));
+    CUDA_TRY(c, sfem_dev_malloc(&op->apack, sizeof(double) * nc * ap8));
     CUDA_TRY(c, cudaMemsetAsync(op->ktmeta, 0, sizeof(uint4) * nc * kts, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(op->apack, 0, sizeof(double) * nc * ap8, c->stream));
     {
@@ -1114,7 +1114,7 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
     int64_t nnz = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&nnz, ptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     int* stats = nullptr;
-    CUDA_TRY(c, cudaMalloc(&stats, sizeof(int) * 4));
+    CUDA_TRY(c, sfem_dev_malloc(&stats, sizeof(int) * 4));
     CUDA_TRY(c, cudaMemsetAsync(stats, 0, sizeof(int) * 4, c->stream));
     static bool attr_set = false;
     if (!attr_set) {
@@ -1130,7 +1130,7 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
     int hstats[4] = {0, 0, 0, 0};
     cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(stats);
+    sfem_dev_free(stats);
     if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: count pass failed: %s", cudaGetErrorString(e));
     if (hstats[2]) return sfem_fail(c, SFEM_ERR_LIMIT, "tileop: a chunk has too many entries or columns");
     op.nnz = nnz;
@@ -1140,10 +1140,10 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
     op.n4 = (op.max_need + 3) & ~3;
     op.e8 = (op.max_ent + 7) & ~7;
     size_t nc = (size_t)nchunks;
-    CUDA_TRY(c, cudaMalloc(&op.desc, sizeof(int) * nc * op.dl));
-    CUDA_TRY(c, cudaMalloc(&op.need, sizeof(int) * nc * op.n4));
-    CUDA_TRY(c, cudaMalloc(&op.ecol, sizeof(unsigned short) * nc * op.e8));
-    CUDA_TRY(c, cudaMalloc(&op.eval, sizeof(double) * nc * op.e8));
+    CUDA_TRY(c, sfem_dev_malloc(&op.desc, sizeof(int) * nc * op.dl));
+    CUDA_TRY(c, sfem_dev_malloc(&op.need, sizeof(int) * nc * op.n4));
+    CUDA_TRY(c, sfem_dev_malloc(&op.ecol, sizeof(unsigned short) * nc * op.e8));
+    CUDA_TRY(c, sfem_dev_malloc(&op.eval, sizeof(double) * nc * op.e8));
     CUDA_TRY(c, cudaMemsetAsync(op.desc, 0, sizeof(int) * nc * op.dl, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(op.need, 0, sizeof(int) * nc * op.n4, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(op.ecol, 0, sizeof(unsigned short) * nc * op.e8, c->stream));
@@ -1162,13 +1162,13 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
 
 int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv) {
     if (op->nchunks <= 0) return SFEM_OK;
-    if (!op->eval_scaled) CUDA_TRY(c, cudaMalloc(&op->eval_scaled, sizeof(double) * (size_t)op->nchunks * op->e8));
+    if (!op->eval_scaled) CUDA_TRY(c, sfem_dev_malloc(&op->eval_scaled, sizeof(double) * (size_t)op->nchunks * op->e8));
     ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
     tile_scale_kernel<<<op->nchunks, 128, 0, c->stream>>>(op->nchunks, op->dl, op->n4, op->e8, op->desc, op->need, op->ecol, op->eval, dinv, op->eval_scaled);
     KCHECK(c);
     if (op->kts > 0) {
         size_t nc = (size_t)op->nchunks;
-        if (!op->apack_scaled) CUDA_TRY(c, cudaMalloc(&op->apack_scaled, sizeof(double) * nc * op->ap8));
+        if (!op->apack_scaled) CUDA_TRY(c, sfem_dev_malloc(&op->apack_scaled, sizeof(double) * nc * op->ap8));
         CUDA_TRY(c, cudaMemsetAsync(op->apack_scaled, 0, sizeof(double) * nc * op->ap8, c->stream));
         tile_dmma_fill_kernel<<<(4 * op->nchunks + 127) / 128, 128, 0, c->stream>>>(op->nchunks, op->dl, op->e8, op->kts, op->ap8, 0, op->desc,
                                                                                    op->ecol, op->eval, op->eval_scaled, op->rgcnt, op->ktmeta,

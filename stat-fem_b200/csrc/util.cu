@@ -39,14 +39,14 @@ void* sfem_scratch(sfem_ctx* c, size_t bytes) {
     if (bytes <= c->scratch_bytes && c->scratch) return c->scratch;
     if (c->scratch) {
         cudaStreamSynchronize(c->stream);
-        cudaFree(c->scratch);
+        sfem_dev_free(c->scratch);
         c->scratch = nullptr;
         c->scratch_bytes = 0;
     }
     size_t want = bytes + bytes / 4 + 4096;
-    if (cudaMalloc(&c->scratch, want) != cudaSuccess) {
+    if (sfem_dev_malloc(&c->scratch, want) != cudaSuccess) {
         cudaGetLastError();
-        if (cudaMalloc(&c->scratch, bytes) != cudaSuccess) {
+        if (sfem_dev_malloc(&c->scratch, bytes) != cudaSuccess) {
             cudaGetLastError();
             c->scratch = nullptr;
             return nullptr;
@@ -182,8 +182,8 @@ __global__ void iota_kernel(int* __restrict__ nodes, int64_t n) {
 // Build cell_start[ncell+1], cell_nodes[n] (both cudaMalloc'd, returned through the out pointers).
 int build_cell_list(sfem_ctx* c, const int* cell_of, int64_t n, int ncell, int** cell_start_out, int** cell_nodes_out) {
     int *start = nullptr, *nodes = nullptr;
-    CUDA_TRY(c, cudaMalloc(&start, sizeof(int) * ((size_t)ncell + 1)));
-    CUDA_TRY(c, cudaMalloc(&nodes, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+    CUDA_TRY(c, sfem_dev_malloc(&start, sizeof(int) * ((size_t)ncell + 1)));
+    CUDA_TRY(c, sfem_dev_malloc(&nodes, sizeof(int) * (size_t)(n > 0 ? n : 1)));
     *cell_start_out = start;
     *cell_nodes_out = nodes;
     if (ncell == 1) {
