@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
 // Dot products (TM_MULT_DOT / TM_JACOBI_DOT) are transposed through a per-warp scratch and accumulated per column in
 // shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
 constexpr int DM_PITCH = 544;     // bytes between staged rows (512 + 32)
-constexpr int DM_KTR = 10;        // k-tiles of a row group held in registers
+constexpr int DM_KTR = 8;         // k-tiles of a row group held in registers
 constexpr int DM_NREC = 4;        // chunk-record ring
 constexpr int DM_HDR = 128;       // mbarriers: full[3] at 0, record[4] at 24, empty[3] at 56, chunk-done[4] at 80
 
@@ -1019,7 +1019,8 @@ int launch_dmma(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int
         cudaFuncSetAttribute(tileop_dmma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         attr_set = true;
     }
-    // persistent grid: two CTAs per SM (register-limited; dmma_stages checked the shared memory)
+    // persistent grid: two CTAs per SM (register-limited; the caller checked the shared memory).  Three CTAs per SM at
+    // 80 registers (launch bounds 256 x 3, two stages) were measured 7 % slower: spills and a shallower pipeline.
     const int64_t want = 2 * (int64_t)SFEM_NUM_SMS;
     int grid = (int)((int64_t)op.nchunks < want ? (int64_t)op.nchunks : want);
     if (nparts) *nparts = grid;
