@@ -7,7 +7,7 @@ One *step* = one full pass of the hot path over one synthetic problem (BASELINE.
        fits run concurrently on separate streams; their mean solves advance together as block solves).
 `value`  : seconds per step with every input already resident in HBM and no result copied back (device-timed).
 `e2e`    : seconds per step through the public drop-in API with HOST buffers (NumPy in, NumPy out).
-`roofline`: the stiffness-operator kernel family (tileop_kernel on the fine level: q = A p, Jacobi sweeps, residual),
+`roofline`: the stiffness-operator kernel family (tileop_dmma_kernel on the fine level: q = A p, Jacobi sweeps, residual),
             timed live with CUDA events inside the timed region; algorithmic bytes per launch are documented in DESIGN.md.
 `--impl reference`: the NumPy/SciPy restatement of the reference (oracle/) on the box's host cores, bounded sample,
             extrapolated linearly to the full workload (the faithful O(n^2) reference cannot run config 2 in full).
@@ -283,7 +283,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": bytes_d2h(prob), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "tileop_kernel on the stiffness matrix (staged-tile SpMM: q=Ap+dot, fused double Jacobi sweep, Jacobi sweep, residual)",
+        "roofline": {"bound": "hbm", "kernel": "tileop_dmma_kernel on the stiffness matrix (staged-tile SpMM on FP64 tensor cores, TMA-staged: q=Ap+dot, fused double Jacobi sweep, Jacobi sweep, residual)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": _read_traffic(), "launches": int(csr_count), "avg_launch_ms": csr_ms / max(csr_count, 1),
                      "peak_source": peak_src},
@@ -325,7 +325,7 @@ class _ProfileHook(object):
 
 
 def _read_traffic():
-    "DRAM bytes per launch of the dominant kernel (TM_JACOBI, 384 columns) from the committed ncu capture, if any"
+    "DRAM bytes per launch of the dominant kernel (tileop_dmma_kernel<TM_JACOBI>, 384 columns) from the committed ncu capture, if any"
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["tileop_kernel_bytes_per_launch"]
     except Exception:
