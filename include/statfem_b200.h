@@ -127,6 +127,16 @@ int sfem_rows_gather(sfem_ctx* ctx, int64_t nrows, const int32_t* rows, int k, c
 int sfem_dgemm_lower(sfem_ctx* ctx, int opA, int opB, int n, int64_t K, double alpha, const double* A, int64_t lda,
                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 int sfem_mirror_lower(sfem_ctx* ctx, int n, double* A, int64_t lda);
+/* W = G Z on FP64 tensor cores (csrc/bsr.cu; replaces PETSc MatMult at ForcingCovariance.py:242 for blocks of
+ * right-hand sides).  sfem_b84_build converts a CSR matrix with ascending column indices per row (device arrays, the
+ * output of sfem_gcov_fill) into 8x4 blocks: 8 consecutive rows x the sorted union of their columns, 4 at a time, as
+ * dense DMMA A operands; *ntiles_out_host receives the number of blocks (32 doubles + 4 indices each).  The handle owns
+ * device memory of the library and is released with sfem_b84_free.  sfem_b84_spmm: Y (n x k, ldy, 16-byte aligned,
+ * ldy even) = G X (n x k, ldx); X and Y must not alias. */
+int sfem_b84_build(sfem_ctx* ctx, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals,
+                   void** matrix_out, int64_t* ntiles_out_host);
+int sfem_b84_spmm(sfem_ctx* ctx, const void* matrix, int k, const double* X, int64_t ldx, double* Y, int64_t ldy);
+int sfem_b84_free(sfem_ctx* ctx, void* matrix);
 /* Self-check hook of the staged-tile operators (csrc/tileop.cu): applies ONE operator of the multigrid hierarchy built
  * by sfem_mg_setup -- which: 0 = level operator, 1 = prolongation from level+1, 2 = restriction to level+1; mode: 0 Y=AX,
  * 1 Y+=AX, 2 Y=AX with dot(X,Y), 3 Jacobi sweep, 4 Jacobi sweep with dot(B,Y), 5 residual B-AX, 6 two sweeps from zero --

@@ -24,6 +24,7 @@ EXPORTS = [
     "sfem_posterior_cov", "sfem_dense_solve", "sfem_cov_matrix", "sfem_axpby", "sfem_profile_enable", "sfem_profile_num_tags",
     "sfem_profile_tag_name", "sfem_profile_read", "sfem_csr_unsym_count", "sfem_csr_unsym_fill", "sfem_rows_axpy",
     "sfem_rows_gather", "sfem_dgemm_lower", "sfem_mirror_lower", "sfem_tile_apply_one",
+    "sfem_b84_build", "sfem_b84_spmm", "sfem_b84_free",
 ]
 
 
@@ -76,6 +77,9 @@ def load_library():
         "sfem_rows_gather": (i32, [vp, i64, vp, i32, vp, i64, vp, i64]),
         "sfem_dgemm_lower": (i32, [vp, i32, i32, i32, i64, f64, vp, i64, vp, i64, f64, vp, i64]),
         "sfem_mirror_lower": (i32, [vp, i32, vp, i64]),
+        "sfem_b84_build": (i32, [vp, i64, vp, vp, vp, C.POINTER(vp), C.POINTER(i64)]),
+        "sfem_b84_spmm": (i32, [vp, vp, i32, vp, i64, vp, i64]),
+        "sfem_b84_free": (i32, [vp, vp]),
         "sfem_tile_apply_one": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64),
                                       C.POINTER(i32)]),
         "sfem_dense_solve": (i32, [vp, i32, i32, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, sz]),
@@ -91,6 +95,7 @@ _lib = None
 _ctx = {}
 _retired_launches = [0]
 _live = []
+USE_BLOCK_FORM = [os.environ.get("SFEM_BLOCK_FORM", "1") != "0"]     # W = G Z through the DMMA block form (csrc/bsr.cu)
 DEVICE_CACHE = [False]     # bench.py's device-resident arm: keep uploaded inputs (A, coords, b, P) in HBM between steps
 
 
@@ -204,6 +209,31 @@ class DeviceCSR(object):
         assert self.indptr.dtype == torch.int64 and self.indices.dtype == torch.int32 and self.data.dtype == torch.float64
         self.nnz = int(self.indices.shape[0])
 
+    # ---- FP64 tensor-core form (csrc/bsr.cu): worth its set-up for wide blocks on matrices with long rows (G)
+    BLOCK_FORM_MIN_COLS = 256
+    BLOCK_FORM_MIN_ROW_NNZ = 16
+
+    def block_form(self):
+        "handle of the 8x4-block form, built on first use"
+        if self.__dict__.get("_b84") is None:
+            h, nt = C.c_void_p(), C.c_int64(0)
+            self.ctx.check(lib().sfem_b84_build(self.ctx.handle, self.shape[0], ptr(self.indptr), ptr(self.indices), ptr(self.data),
+                                                C.byref(h), C.byref(nt)))
+            self._b84, self.block_tiles = h, int(nt.value)
+        return self._b84
+
+    def release_block_form(self):
+        h = self.__dict__.get("_b84")
+        if h is not None and self.ctx.handle:
+            lib().sfem_b84_free(self.ctx.handle, h)
+        self._b84 = None
+
+    def __del__(self):
+        try:
+            self.release_block_form()
+        except Exception:
+            pass
+
     def matmul(self, X, out=None):
         "Y = S X for a device block X (nrows_in x k) or vector"
         ctx = self.ctx
@@ -213,6 +243,10 @@ class DeviceCSR(object):
         k = int(X2.shape[1])
         Y = out if out is not None else ctx.empty((self.shape[0], k))
         Y2 = Y.reshape(-1, 1) if Y.dim() == 1 else Y
+        if (USE_BLOCK_FORM[0] and k >= self.BLOCK_FORM_MIN_COLS and self.shape[0] == self.shape[1]
+                and self.nnz >= self.BLOCK_FORM_MIN_ROW_NNZ * self.shape[0] and Y2.stride(0) % 2 == 0 and Y2.data_ptr() % 16 == 0):
+            ctx.check(lib().sfem_b84_spmm(ctx.handle, self.block_form(), k, ptr(X2), int(X2.stride(0)), ptr(Y2), int(Y2.stride(0))))
+            return Y
         ctx.check(lib().sfem_spmm_csr(ctx.handle, self.shape[0], self.nnz, ptr(self.indptr), ptr(self.indices), ptr(self.data), k,
                                       ptr(X2), int(X2.stride(0)), ptr(Y2), int(Y2.stride(0))))
         return Y.reshape(-1) if vec and out is None else Y

@@ -28,6 +28,11 @@ int unsym_fill(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, c
                const int64_t* rowpos, int32_t* rows_out, int64_t* eptr_out, int32_t* eidx_out, double* eval_out);
 int mg_tile_apply_one(sfem_ctx* c, int level, int which, int mode, int k, const double* X, const double* B, double* Y,
                       double* partials, int* nparts_host, int use_dmma, int64_t* rows_out, int64_t* cols_out, int* has_dmma_out);
+struct B84Matrix;
+int b84_build(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, const double* val, B84Matrix** out);
+int b84_spmm(sfem_ctx* c, const B84Matrix* m, int k, const double* X, int64_t ldx, double* Y, int64_t ldy);
+void b84_free(B84Matrix* m);
+int64_t b84_num_tiles(const B84Matrix* m);
 int rows_axpy(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx, double* Y, int64_t ldy);
 int rows_gather(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X, int64_t ldx);
 int mirror_lower(sfem_ctx* c, int n, double* A, int64_t ld);
@@ -277,6 +282,26 @@ int sfem_tile_apply_one(sfem_ctx* c, int level, int which, int mode, int k, cons
     return mg_tile_apply_one(c, level, which, mode, k, X, B, Y, partials, nparts_out_host, use_tensor_form, rows_out_host,
                              cols_out_host, tensor_form_out_host);
 }
+int sfem_b84_build(sfem_ctx* c, int64_t n, const int64_t* indptr, const int32_t* indices, const double* vals, void** matrix_out,
+                   int64_t* ntiles_out_host) {
+    GUARD(c);
+    if (!matrix_out) return sfem_fail(c, SFEM_ERR_ARG, "b84_build: no output handle");
+    B84Matrix* m = nullptr;
+    int rc = b84_build(c, n, indptr, indices, vals, &m);
+    *matrix_out = m;
+    if (ntiles_out_host) *ntiles_out_host = b84_num_tiles(m);
+    return rc;
+}
+int sfem_b84_spmm(sfem_ctx* c, const void* matrix, int k, const double* X, int64_t ldx, double* Y, int64_t ldy) {
+    GUARD(c);
+    return b84_spmm(c, static_cast<const B84Matrix*>(matrix), k, X, ldx, Y, ldy);
+}
+int sfem_b84_free(sfem_ctx* c, void* matrix) {
+    GUARD(c);
+    b84_free(static_cast<B84Matrix*>(matrix));
+    return SFEM_OK;
+}
+
 int sfem_mirror_lower(sfem_ctx* c, int n, double* A, int64_t lda) {
     GUARD(c);
     return mirror_lower(c, n, A, lda);

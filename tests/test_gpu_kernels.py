@@ -224,6 +224,40 @@ def test_block_solve_matches_direct(env, dim, nodes, pc):
         assert max(ls.block_iterations) <= 60
 
 
+@pytest.mark.parametrize("dim,nodes,lfac,k", [(2, 65, 1.5, 256), (2, 50, 2.2, 72), (3, 14, 0.8, 130), (1, 203, 3.0, 64)])
+def test_block_form_spmm(env, dim, nodes, lfac, k):
+    """W = G Z through the 8x4-block (DMMA) form of csrc/bsr.cu against SciPy's CSR product and against the scalar CSR
+    kernel: ragged row groups (n not a multiple of 8), column counts that are not multiples of 64, 1-D / 2-D / 3-D G."""
+    import torch
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    _lib, ctx, lib = env
+    V, A, b = fem.poisson_problem(nodes, dim)
+    h = 1. / (nodes - 1)
+    sig = np.log(2.e-2)
+    G = stat_fem.ForcingCovariance(V, sig, np.log(lfac * h), 1.e-3, 1.e-8 * h ** (2 * dim) * np.exp(2 * sig))
+    G.assemble()
+    ip, ix, v = G.G.to_host()
+    n = V.dim()
+    S = sp.csr_matrix((v, ix, ip), shape=(n, n))
+    rng = np.random.default_rng(k)
+    X = rng.normal(size=(n, k))
+    Xd = G.G.ctx.to_device(X, np.float64)
+    Y = torch.full((n, k), float("nan"), dtype=torch.float64, device="cuda")
+    G.G.ctx.check(lib.sfem_b84_spmm(G.G.ctx.handle, G.G.block_form(), k, _lib.ptr(Xd), k, _lib.ptr(Y), k))
+    ref = S @ X
+    assert G.G.block_tiles * 32 >= S.nnz and G.G.block_tiles > 0
+    assert relerr(Y.cpu().numpy(), ref) < 1e-13
+    was = _lib.USE_BLOCK_FORM[0]
+    try:
+        _lib.USE_BLOCK_FORM[0] = False
+        Y0 = G.G.matmul(Xd).cpu().numpy()          # scalar CSR kernel
+    finally:
+        _lib.USE_BLOCK_FORM[0] = was
+    assert relerr(Y.cpu().numpy(), Y0) < 1e-13
+    print("n=%d nnz/row=%.1f block fill %.2f" % (n, S.nnz / n, S.nnz / (32. * G.G.block_tiles)))
+
+
 # modes of the staged-tile kernels (csrc/tileop.cuh): name -> (code, needs right-hand side, returns dot partials)
 TILE_MODES = {"mult": (0, False, False), "mult_add": (1, True, False), "mult_dot": (2, False, True), "jacobi": (3, True, False),
               "jacobi_dot": (4, True, True), "resid": (5, True, False), "presmooth2": (6, False, False)}

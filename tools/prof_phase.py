@@ -2,7 +2,7 @@
 
     python tools/prof_phase.py solve [nodes] [ncols] [dim]   one block PCG solve of `ncols` sensor columns
     python tools/prof_phase.py dense [n_obs] [reps]          logposterior + gradient evaluations at n_obs sensors
-    python tools/prof_phase.py gcov  [nodes] [dim]           forcing-covariance assembly + W = G Z (64 columns)
+    python tools/prof_phase.py gcov  [nodes] [dim] [lfac] [ncol]   forcing-covariance assembly + W = G Z, both kernel forms
 
 Prints device time per phase (CUDA events around the call) and the library's per-kernel-family table."""
 import os
@@ -111,13 +111,20 @@ def phase_gcov(argv):
     print("G assembly n=%d: %.2f ms device, %.2f ms wall, nnz %d (%.1f/row)" % (V.dim(), ms, 1e3 * (time.perf_counter() - t),
                                                                                   G.G.nnz, G.G.nnz / V.dim()))
     ctx = G.G.ctx
-    Z = ctx.empty((V.dim(), 64)).normal_()
-    W = ctx.empty((V.dim(), 64))
-    G.G.matmul(Z, out=W)
-    ms, _ = dev_time(lambda: G.G.matmul(Z, out=W), 3)
+    ncol = int(argv[3]) if len(argv) > 3 else 512
+    Z = ctx.empty((V.dim(), ncol)).normal_()
+    W = ctx.empty((V.dim(), ncol))
     nnz = G.G.nnz
-    print("W = G Z (64 columns): %.2f ms  %.1f GB/s algorithmic  %.2f TFLOP/s" %
-          (ms, (16. * V.dim() * 64 + 12. * nnz) / ms * 1e-6, 2. * nnz * 64 / ms * 1e-9))
+    for form in (False, True):
+        _lib.USE_BLOCK_FORM[0] = form
+        if form:
+            ms, _ = dev_time(G.G.block_form)
+            print("8x4-block form: %.2f ms to build, %d blocks, fill %.2f" % (ms, G.G.block_tiles, nnz / (32. * G.G.block_tiles)))
+        G.G.matmul(Z, out=W)
+        ms, _ = dev_time(lambda: G.G.matmul(Z, out=W), 3)
+        print("W = G Z (%d columns, %s): %.2f ms  %.1f GB/s algorithmic  %.2f TFLOP/s" %
+              (ncol, "DMMA block form" if form else "scalar CSR kernel", ms,
+               (16. * V.dim() * ncol + 12. * nnz * ((ncol + 63) // 64)) / ms * 1e-6, 2. * nnz * ncol / ms * 1e-9))
 
 
 if __name__ == "__main__":
