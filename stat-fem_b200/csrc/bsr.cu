@@ -58,30 +58,129 @@ __device__ __forceinline__ int merge_group(int64_t n, int64_t g, const int64_t* 
     return pos;
 }
 
-__global__ void b84_count_kernel(int64_t n, int64_t nrg, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                 int64_t* __restrict__ ntile) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Builder: one warp per row group.  The distinct columns of the group are found with a bitmap over its column span in
+// shared memory (atomicOr per entry, popcount prefix per word): every entry then knows its position in the sorted union
+// without any serial merge.  Groups whose columns span more than B84_SPAN indices fall back to the merge on one lane.
+constexpr int B84_SPAN = 65536;                 // bitmap bits per warp (8 KB) + as many prefix entries / 32 (8 KB)
+constexpr int B84_WARPS = 2;                    // warps per builder CTA (32 KB of static shared memory)
+
+struct GroupSpan { int lo, hi; };
+__device__ __forceinline__ GroupSpan group_span(int64_t n, int64_t g, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int lane) {
+    int lo = INT_MAX, hi = -1;
+    if (lane < 8) {
+        const int64_t row = g * 8 + lane;
+        if (row < n && ptr[row] < ptr[row + 1]) { lo = idx[ptr[row]]; hi = idx[ptr[row + 1] - 1]; }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    GroupSpan s;
+    s.lo = __shfl_sync(0xffffffffu, lo, 0);
+    s.hi = __shfl_sync(0xffffffffu, hi, 0);
+    return s;
+}
+// marks the columns of the group in bm (words [0, nw) zeroed first); all lanes of the warp
+__device__ __forceinline__ void group_bitmap(int64_t n, int64_t g, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int lo, int nw,
+                                             unsigned* bm, int lane) {
+    for (int w = lane; w < nw; w += 32) bm[w] = 0u;
+    __syncwarp();
+    for (int r = 0; r < 8; ++r) {
+        const int64_t row = g * 8 + r;
+        if (row >= n) break;
+        for (int64_t e = ptr[row] + lane; e < ptr[row + 1]; e += 32) {
+            const int cb = idx[e] - lo;
+            atomicOr(&bm[cb >> 5], 1u << (cb & 31));
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * B84_WARPS) b84_count_kernel(int64_t n, int64_t nrg, const int64_t* __restrict__ ptr,
+                                                                   const int32_t* __restrict__ idx, int64_t* __restrict__ ntile) {
+    __shared__ unsigned bms[B84_WARPS][B84_SPAN / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * B84_WARPS + warp;
     if (g >= nrg) return;
-    const int u = merge_group(n, g, ptr, idx, [](int, int, int, int64_t) {});
-    ntile[g] = (u + 3) >> 2;
+    const GroupSpan sp = group_span(n, g, ptr, idx, lane);
+    int u = 0;
+    if (sp.hi < sp.lo) u = 0;
+    else if (sp.hi - sp.lo >= B84_SPAN) {
+        if (lane == 0) u = merge_group(n, g, ptr, idx, [](int, int, int, int64_t) {});
+        u = __shfl_sync(0xffffffffu, u, 0);
+    } else {
+        const int nw = ((sp.hi - sp.lo) >> 5) + 1;
+        group_bitmap(n, g, ptr, idx, sp.lo, nw, bms[warp], lane);
+        for (int w = lane; w < nw; w += 32) u += __popc(bms[warp][w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+    }
+    if (lane == 0) ntile[g] = (u + 3) >> 2;
 }
 
 // vals must be zero on entry
-__global__ void b84_fill_kernel(int64_t n, int64_t nrg, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                const double* __restrict__ val, const int64_t* __restrict__ tptr, int32_t* __restrict__ cols,
-                                double* __restrict__ vals) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * B84_WARPS) b84_fill_kernel(int64_t n, int64_t nrg, const int64_t* __restrict__ ptr,
+                                                                  const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                                                  const int64_t* __restrict__ tptr, int32_t* __restrict__ cols,
+                                                                  double* __restrict__ vals) {
+    __shared__ unsigned bms[B84_WARPS][B84_SPAN / 32];
+    __shared__ int pres[B84_WARPS][B84_SPAN / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * B84_WARPS + warp;
     if (g >= nrg) return;
     const int64_t t0 = tptr[g];
-    int lastc = 0;
-    const int u = merge_group(n, g, ptr, idx, [&](int pos, int col, int r, int64_t e) {
-        const int64_t t = t0 + (pos >> 2);
-        const int q = pos & 3;
-        cols[t * 4 + q] = col;
-        vals[t * 32 + r * 4 + q] += val[e];      // repeated columns of a row add up
-        lastc = col;
-    });
-    for (int pos = u; pos & 3; ++pos) cols[(t0 + (pos >> 2)) * 4 + (pos & 3)] = lastc;      // padding: a valid row of Z, zero block column
+    const GroupSpan sp = group_span(n, g, ptr, idx, lane);
+    if (sp.hi < sp.lo) return;
+    if (sp.hi - sp.lo >= B84_SPAN) {          // wide group: serial merge on one lane
+        if (lane == 0) {
+            int lastc = 0;
+            const int u = merge_group(n, g, ptr, idx, [&](int pos, int col, int r, int64_t e) {
+                const int64_t t = t0 + (pos >> 2);
+                const int q = pos & 3;
+                cols[t * 4 + q] = col;
+                vals[t * 32 + r * 4 + q] += val[e];
+                lastc = col;
+            });
+            for (int pos = u; pos & 3; ++pos) cols[(t0 + (pos >> 2)) * 4 + (pos & 3)] = lastc;
+        }
+        return;
+    }
+    unsigned* bm = bms[warp];
+    int* pre = pres[warp];
+    const int nw = ((sp.hi - sp.lo) >> 5) + 1;
+    group_bitmap(n, g, ptr, idx, sp.lo, nw, bm, lane);
+    // exclusive prefix of the word popcounts: position of a word's first column in the sorted union
+    int running = 0;
+    for (int base = 0; base < nw; base += 32) {
+        const int w = base + lane;
+        const int cnt = w < nw ? __popc(bm[w]) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (w < nw) pre[w] = running + incl - cnt;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    const int u = running;
+    for (int r = 0; r < 8; ++r) {
+        const int64_t row = g * 8 + r;
+        if (row >= n) break;
+        for (int64_t e = ptr[row] + lane; e < ptr[row + 1]; e += 32) {
+            const int col = idx[e];
+            const int cb = col - sp.lo;
+            const int pos = pre[cb >> 5] + __popc(bm[cb >> 5] & ((1u << (cb & 31)) - 1u));
+            const int64_t t = t0 + (pos >> 2);
+            const int q = pos & 3;
+            cols[t * 4 + q] = col;                                      // every row holding this column writes the same value
+            atomicAdd(&vals[t * 32 + r * 4 + q], val[e]);               // repeated columns of a row add up
+        }
+    }
+    if (lane == 0)
+        for (int pos = u; pos & 3; ++pos) cols[(t0 + (pos >> 2)) * 4 + (pos & 3)] = sp.hi;      // padding: a valid row of X, zero block column
 }
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -220,7 +319,7 @@ int b84_build(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, co
         return fail(sfem_fail(c, SFEM_ERR_CUDA, "b84_build: out of memory"));
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
-        b84_count_kernel<<<(unsigned)cdiv64(m->nrg, 128), 128, 0, c->stream>>>(n, m->nrg, ptr, idx, ntile);
+        b84_count_kernel<<<(unsigned)cdiv64(m->nrg, B84_WARPS), 32 * B84_WARPS, 0, c->stream>>>(n, m->nrg, ptr, idx, ntile);
         c->launches++;
         rc = exclusive_scan<int64_t>(c, ntile, m->nrg, m->tptr, sums);
     }
@@ -241,7 +340,7 @@ int b84_build(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, co
     cudaMemsetAsync(m->vals, 0, sizeof(double) * 32 * nt, c->stream);
     {
         ProfScope ps(c, TAG_SETUP, 0.0, 0.0);
-        b84_fill_kernel<<<(unsigned)cdiv64(m->nrg, 128), 128, 0, c->stream>>>(n, m->nrg, ptr, idx, val, m->tptr, m->cols, m->vals);
+        b84_fill_kernel<<<(unsigned)cdiv64(m->nrg, B84_WARPS), 32 * B84_WARPS, 0, c->stream>>>(n, m->nrg, ptr, idx, val, m->tptr, m->cols, m->vals);
         c->launches++;
     }
     cudaError_t e = cudaGetLastError();

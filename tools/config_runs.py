@@ -44,9 +44,15 @@ def c4(nodes=2048, nobs=512):
     Z = ls.solver.ctx.empty((n, nobs))
     ms_z, _ = dev_ms(lambda: ls.solver.solve_columns(ls.im.csc, 0, nobs, Z))
     W = ctx.empty((n, nobs))
+    _lib.USE_BLOCK_FORM[0] = False                    # scalar CSR kernel (spmm.cu)
+    G.G.matmul(Z, out=W)
+    ms_w0, _ = dev_ms(lambda: G.G.matmul(Z, out=W))
+    _lib.USE_BLOCK_FORM[0] = True                     # 8x4-block form on FP64 tensor cores (bsr.cu)
+    ms_build, _ = dev_ms(G.G.block_form)
     G.G.matmul(Z, out=W)
     ms_w, _ = dev_ms(lambda: G.G.matmul(Z, out=W))
     out = dict(config="c4", n=n, nnzG=int(nnz), nnz_per_row=nnz / n, n_obs=nobs,
+               GZ_scalar_csr_ms=ms_w0, block_form_build_ms=ms_build, block_fill=nnz / (32. * G.G.block_tiles),
                G_assembly_ms=ms_g, G_assembly_GBs=(12. * nnz + 8. * (n + 1) + 24. * n) / ms_g * 1e-6,
                solve_ms=ms_z, cg_iterations=list(ls.solver.block_iterations), relres_max=float(ls.solver.last_relres.max()),
                GZ_ms=ms_w, GZ_TFLOPs=2. * nnz * nobs / ms_w * 1e-9, GZ_GBs=(16. * n * nobs + 12. * nnz * ((nobs + 63) // 64)) / ms_w * 1e-6,
