@@ -1,4 +1,4 @@
-"""World-size-2 CPU test (gloo) of the host-side sharding logic: PETSc-style column ownership, the all-gather /
+"""World-size 2-4 CPU tests (gloo) of the host-side sharding logic: PETSc-style column ownership, the all-gather /
 accumulate / gather-to-root exchange of the sharded covariance assembly (solving_utils.sharded_wtz, the step that
 replaces solving_utils.py:117-159 of the reference), object broadcast and allreduce.  The GEMM is a torch.mm stand-in
 here; on the GPU the same function is driven with the DMMA GEMM of the library."""
@@ -59,9 +59,10 @@ def _worker(rank, world, port, n, n_left, n_right, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,n_left,n_right", [(4000, 7, 7), (3001, 5, 9), (2500, 1, 3)])
-def test_sharded_wtz_world2(n, n_left, n_right):
-    world = 2
+@pytest.mark.parametrize("world,n,n_left,n_right", [(2, 4000, 7, 7), (2, 3001, 5, 9), (2, 2500, 1, 3), (3, 2200, 8, 8), (4, 2100, 6, 10),
+                                                    (4, 1500, 3, 3)])
+def test_sharded_wtz(world, n, n_left, n_right):
+    "world sizes 2-4, uneven column splits, ranks that own no column at all (3 columns over 4 ranks)"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
