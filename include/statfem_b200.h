@@ -127,6 +127,11 @@ int sfem_rows_gather(sfem_ctx* ctx, int64_t nrows, const int32_t* rows, int k, c
 int sfem_dgemm_lower(sfem_ctx* ctx, int opA, int opB, int n, int64_t K, double alpha, const double* A, int64_t lda,
                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 int sfem_mirror_lower(sfem_ctx* ctx, int n, double* A, int64_t lda);
+/* Sharded form of the same split (ensemble ranks own contiguous column blocks, solving_utils.py:117-123): every
+ * unordered pair of different ownership blocks of the symmetric term is computed by ONE rank (half-ring schedule), so
+ * the gathered n x n array holds block (r, s) or block (s, r) and zeros in the other; sfem_sym_fold adds each
+ * off-diagonal-block entry to its transpose in place (nblocks = ensemble size, PETSc's contiguous ownership rule). */
+int sfem_sym_fold(sfem_ctx* ctx, int n, int nblocks, double* A, int64_t lda);
 /* W = G Z on FP64 tensor cores (csrc/bsr.cu; replaces PETSc MatMult at ForcingCovariance.py:242 for blocks of
  * right-hand sides).  sfem_b84_build converts a CSR matrix with ascending column indices per row (device arrays, the
  * output of sfem_gcov_fill) into 8x4 blocks: 8 consecutive rows x the sorted union of their columns, 4 at a time, as
@@ -166,6 +171,11 @@ int sfem_cov_matrix(sfem_ctx* ctx, int m, int n, int dim, const double* X1, cons
                     int which, double* M_out);
 /* z = a x + b y on device vectors (y may be NULL): the mesh-space combinations of LinearSolver.py:287, 303-305. */
 int sfem_axpby(sfem_ctx* ctx, int64_t n, double a, const double* x, double b, const double* y, double* z);
+/* Y[n x ns] = X[n x k] C[k x ns] for a few columns ns (row-major, leading dimensions in elements): v = W c with the
+ * resident W = G Z, so that A^-1 G A^-1 P c = A^-1 (W c) costs one mesh-space solve instead of the two of
+ * solving_utils.py:49-53 in every term of the posterior mean (LinearSolver.py:283-301). */
+int sfem_skinny_gemm(sfem_ctx* ctx, int64_t n, int k, int ns, const double* X, int64_t ldx, const double* C, int64_t ldc,
+                     double* Y, int64_t ldy);
 size_t sfem_dense_workspace_bytes(int n_obs);
 /* Negative log marginal likelihood and (if grad_out_host != NULL) its gradient at theta_host = (log rho, log sigma_eta,
  * log l_eta): LinearSolver.logposterior / logpost_deriv. */

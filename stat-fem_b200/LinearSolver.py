@@ -52,6 +52,7 @@ class LinearSolver(object):
         self.current_logpost = None
         # device mirrors + evaluation cache
         self._x_dev = self._mu_dev = self._Cu_dev = None
+        self._W_dev = self._W_cols = None      # this rank's block of W = G A^-1 P, kept by solve_prior (keep_factors)
         self._dense_work = None
         self._cache = None
         self.fuse_gradient = False      # set by estimate_params_MAP: evaluate value and gradient in one pass
@@ -78,6 +79,7 @@ class LinearSolver(object):
         other._owns_dense_ctx = bool(private_stream)
         other._data_dev = None
         other.n_logpost_evals = 0
+        other._parent = self          # the clone borrows im / solver / prior: keep their owner (and its __del__) alive
         return other
 
     @property
@@ -132,7 +134,10 @@ class LinearSolver(object):
     def solve_prior(self):
         "prior mean and covariance at the sensors (LinearSolver.py:185-222)"
         ctx = self.solver.ctx
-        Cu_dev = interp_covariance_to_data(self.im, self.G, self.solver, self.im, self.ensemble_comm, return_device=True)
+        keep = {} if self._keep_factors() else None
+        Cu_dev = interp_covariance_to_data(self.im, self.G, self.solver, self.im, self.ensemble_comm, return_device=True,
+                                           keep=keep)
+        self._W_dev, self._W_cols = (keep["W"], keep["cols"]) if keep is not None else (None, None)
         self.x = fem.Function(self.G.function_space)
         if self.ensemble_comm.rank == 0:
             bf = self.b.function if isinstance(self.b, fem.Vector) else self.b
@@ -152,9 +157,78 @@ class LinearSolver(object):
         self._cache = None
         return self.mu, self.Cu
 
+    def _keep_factors(self):
+        "keep this rank's block of W = G A^-1 P after solve_prior?  (solver parameter ``keep_factors``; default: if it fits)"
+        flag = self.solver.keep_factors
+        if flag is not None:
+            return bool(flag)
+        import torch
+        lo, hi = self.ensemble_comm.column_range(self.data.get_n_obs())
+        total = torch.cuda.get_device_properties(self.solver.ctx.tdev).total_memory
+        return 8. * self.solver.n * (hi - lo) <= 0.25 * total
+
+    def _aga_p(self, Cmat, collective):
+        """A^-1 G A^-1 P C for a block C (n_obs x ns, device) of data-space vectors -> (n x ns) on the ensemble root.
+        With the resident W = G A^-1 P (solve_prior) this is W C followed by ONE block solve; the columns of W are
+        spread over the ensemble like the sensor columns, so with ``collective`` every rank multiplies its block and the
+        partial sums are reduced on the root (all ranks must call).  Without W: the two solves of solving_utils.py:49-53
+        around G, on the root alone."""
+        sp, ctx, lib = self.solver, self.solver.ctx, _lib.lib()
+        comm = self.ensemble_comm
+        ns = int(Cmat.shape[1])
+        W = self.__dict__.get("_W_dev")
+        have_all = W is not None and (comm.size == 1 or collective)
+        if have_all:
+            lo, hi = self._W_cols
+            V = ctx.zeros((sp.n, ns))
+            if hi > lo:
+                Cl = Cmat[lo:hi]
+                ctx.check(lib.sfem_skinny_gemm(ctx.handle, sp.n, hi - lo, ns, _lib.ptr(W), int(W.stride(0)), _lib.ptr(Cl),
+                                               int(Cl.stride(0)), _lib.ptr(V), ns))
+            if comm.size > 1:
+                comm.reduce_tensor(V, root=0)
+            if comm.rank != 0:
+                return None
+            X = ctx.empty((sp.n, ns))
+            sp.solve_block(V, X)
+            return X
+        if comm.rank != 0:
+            return None
+        X = ctx.empty((sp.n, ns))
+        sp.solve_block(self.im.csr.matmul(Cmat.contiguous()), X)
+        Wb = self.G.G.matmul(X)
+        sp.solve_block(Wb, X)
+        return X
+
+    def _cu_t_times(self, T, rhos):
+        "rho_s Cu^T T[:, s] + mu for every column s (n_obs x ns): P^T (rho A^-1 G A^-1 P t + x) without touching the mesh"
+        import torch
+        ctx, lib = self.solver.ctx, _lib.lib()
+        n, ns = int(T.shape[0]), int(T.shape[1])
+        out = self._mu_dev[:, None].repeat(1, ns).contiguous()
+        Ts = (T * torch.as_tensor(rhos, dtype=torch.float64, device=T.device)[None, :]).contiguous()
+        ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, n, ns, n, 1.0, _lib.ptr(self._Cu_dev), n, _lib.ptr(Ts), ns,
+                                 1.0, _lib.ptr(out), ns))
+        return out
+
     def _dense_solve(self, rho2, with_Cu, b_dev):
-        d = self._data_device()
+        """(K_eta + unc^2 I [+ rho2 Cu])^-1 b on this solver's dense context.  A clone with a private stream
+        (``clone_for_data(private_stream=True)``) runs it there: unless the caller already made that stream current
+        (fit_snapshots / solve_posterior_snapshots do), the right-hand side -- produced on the main stream -- is
+        awaited first and the result is complete before the main stream goes on."""
+        import torch
         ctx = self.dctx
+        side = ctx.tstream is not None and torch.cuda.current_stream(ctx.tdev) != ctx.tstream
+        if side:
+            self.solver.ctx.sync()
+            with torch.cuda.stream(ctx.tstream):
+                out = self._dense_solve_on(ctx, rho2, with_Cu, b_dev)
+            ctx.tstream.synchronize()
+            return out
+        return self._dense_solve_on(ctx, rho2, with_Cu, b_dev)
+
+    def _dense_solve_on(self, ctx, rho2, with_Cu, b_dev):
+        d = self._data_device()
         out = ctx.empty((self.data.get_n_obs(),))
         work, nbytes = self._work()
         ctx.check(_lib.lib().sfem_dense_solve(ctx.handle, self.data.get_n_obs(), self.data.get_n_dim(), _lib.ptr(d["coords"]),
@@ -180,21 +254,25 @@ class LinearSolver(object):
         rho = np.exp(self.params[0])
         scalefact = rho if scale_mean else 1.
         if self.ensemble_comm.rank == 0:
+            # The reference's chain (LinearSolver.py:259-305)
+            #   t1 = Kd^-1 y,  m2 = rho A^-1 G A^-1 P t1 + x,  d2 = (Kd + rho^2 Cu)^-1 P^T m2,  m3 = A^-1 G A^-1 P d2,
+            #   mean = sf (m2 - rho^2 m3)
+            # with P^T A^-1 G A^-1 P = Cu^T (the cached prior) and both mesh-space terms folded into one:
+            #   mean = sf (x + A^-1 G A^-1 P (rho t1 - rho^2 d2)),   P^T m2 = rho Cu^T t1 + mu.
             d = self.data.device()
             try:
                 t1 = self._dense_solve(0., False, d["data"])
             except LinAlgError:
                 raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy")
-            m1 = self.im.csr.matmul(t1)
-            m2 = self._axpby(rho, _aga_device(self.G, self.solver, m1), 1., self._x_dev)
-            d1 = self.im.csc.matmul(m2)
+            d1 = self._cu_t_times(t1.reshape(-1, 1), [rho]).reshape(-1)
             try:
                 d2 = self._dense_solve(rho ** 2, True, d1)
             except LinAlgError:
                 raise LinAlgError("Error attempting to compute the Cholesky factorization of the model discrepancy "
                                   "plus forcing covariance")
-            m3 = _aga_device(self.G, self.solver, self.im.csr.matmul(d2))
-            out = self._axpby(scalefact, m2, -scalefact * rho ** 2, m3)
+            coef = self._axpby(rho, t1, -rho ** 2, d2)
+            m = self._aga_p(coef.reshape(-1, 1), collective=False).reshape(-1)
+            out = self._axpby(scalefact, m, scalefact, self._x_dev)
             xf = x.function if isinstance(x, fem.Vector) else x
             xf.data[:] = out.cpu().numpy()
 
@@ -416,10 +494,12 @@ class LinearSolver(object):
 
 def solve_posterior_snapshots(solvers, xs, scale_mean=False):
     """Posterior means on the mesh for several fitted LinearSolvers that share one prior (``clone_for_data``): the
-    arithmetic of ``solve_posterior`` (LinearSolver.py:259-305) for every snapshot, with the 4 mesh-space solves of
-    each snapshot advanced together as 4 block solves.  On several processes whose prior has been shared
-    (``share_prior``, done by ``fit_snapshots``) the snapshots are dealt out round-robin and the means are collected on
-    rank 0.  ``xs[s]`` receives the mean of snapshot s on the ensemble root.  Extension over the reference API (which
+    arithmetic of ``solve_posterior`` (LinearSolver.py:259-305) for every snapshot.  With W = G A^-1 P resident the
+    four mesh-space solves of a snapshot collapse into one (see ``solve_posterior``), and the solves of all snapshots
+    advance together as ONE block solve on the root.  On several processes whose prior has been shared
+    (``share_prior``, done by ``fit_snapshots``) the dense data-space solves of the snapshots are dealt out round-robin;
+    every rank multiplies its column block of W and the partial sums are reduced on rank 0 (collective: every rank of
+    the ensemble must call).  ``xs[s]`` receives the mean of snapshot s on the ensemble root.  Extension over the reference API (which
     handles one data set per LinearSolver)."""
     import torch
     if not isinstance(bool(scale_mean), bool):
@@ -445,7 +525,6 @@ def solve_posterior_snapshots(solvers, xs, scale_mean=False):
         sub = [solvers[i] for i in mine]
         ns = len(sub)
         rhos = [float(np.exp(ls.params[0])) for ls in sub]
-        sfs = [r if scale_mean else 1. for r in rhos]
 
         def dense_cols(rho2s, with_Cu, rhs_cols):
             """one dense data-space solve per snapshot; clones with a private stream run theirs concurrently (one host
@@ -485,28 +564,23 @@ def solve_posterior_snapshots(solvers, xs, scale_mean=False):
                 out[:, s_] = cols[s_]
             return out
 
-        def aga(M):      # A^-1 G A^-1 on a block of columns, Dirichlet lifting off (solving_utils.py:46-57)
-            X = ctx.empty((n, ns))
-            sp.solve_block(M, X)
-            Wb = G.G.matmul(X)
-            sp.solve_block(Wb, X)
-            return X
-
         T1 = dense_cols([0.] * ns, False, [ls._data_device()["data"] for ls in sub])
-        M2 = aga(im.csr.matmul(T1))                                     # (n x ns)
-        M2 = M2 * torch.tensor(rhos, dtype=torch.float64, device=M2.device)[None, :] + base._x_dev[:, None]
-        D1 = im.csc.matmul(M2.contiguous())                             # (n_obs x ns)
+        D1 = base._cu_t_times(T1, rhos)                                 # P^T (rho A^-1 G A^-1 P t1 + x), (n_obs x ns)
         D2 = dense_cols([r * r for r in rhos], True, [D1[:, s].contiguous() for s in range(ns)])
-        M3 = aga(im.csr.matmul(D2))
-        for s, i in enumerate(mine):
-            outs[i] = (sfs[s] * M2[:, s] - sfs[s] * rhos[s] ** 2 * M3[:, s]).contiguous()
-    for i, x in enumerate(xs):
-        owner = i % comm.size if shared else 0
-        if shared and owner != 0:       # bring the mean of a snapshot computed elsewhere to the root
-            if comm.rank == owner:
-                comm.send_tensor(outs[i], dst=0)
-            elif comm.rank == 0:
-                outs[i] = comm.recv_tensor(ctx.empty((n,)), src=owner)
-        if comm.rank == 0:
+        rt = torch.tensor(rhos, dtype=torch.float64, device=T1.device)[None, :]
+        coef_mine = T1 * rt - D2 * (rt * rt)                            # rho t1 - rho^2 d2 per snapshot
+    # every snapshot's coefficient vector on every rank (the blocks of W are spread over the ranks), then ONE block
+    # solve for all snapshots on the root:  mean_s = sf_s (x + A^-1 W coef_s)
+    nsnap = len(solvers)
+    coef = ctx.zeros((nobs, nsnap))
+    if mine:
+        coef[:, mine] = coef_mine
+    if comm.size > 1:
+        comm.allreduce_tensor(coef)
+    X = base._aga_p(coef, collective=True)
+    if comm.rank == 0:
+        for i, (x, ls) in enumerate(zip(xs, solvers)):
+            sf = float(np.exp(ls.params[0])) if scale_mean else 1.
+            out = sf * (X[:, i] + base._x_dev)
             xf = x.function if isinstance(x, fem.Vector) else x
-            xf.data[:] = outs[i].cpu().numpy()
+            xf.data[:] = out.cpu().numpy()

@@ -24,7 +24,7 @@ EXPORTS = [
     "sfem_posterior_cov", "sfem_dense_solve", "sfem_cov_matrix", "sfem_axpby", "sfem_profile_enable", "sfem_profile_num_tags",
     "sfem_profile_tag_name", "sfem_profile_read", "sfem_csr_unsym_count", "sfem_csr_unsym_fill", "sfem_rows_axpy",
     "sfem_rows_gather", "sfem_dgemm_lower", "sfem_mirror_lower", "sfem_tile_apply_one",
-    "sfem_b84_build", "sfem_b84_spmm", "sfem_b84_free",
+    "sfem_b84_build", "sfem_b84_spmm", "sfem_b84_free", "sfem_skinny_gemm", "sfem_sym_fold",
 ]
 
 
@@ -82,6 +82,8 @@ def load_library():
         "sfem_b84_free": (i32, [vp, vp]),
         "sfem_tile_apply_one": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64),
                                       C.POINTER(i32)]),
+        "sfem_sym_fold": (i32, [vp, i32, i32, vp, i64]),
+        "sfem_skinny_gemm": (i32, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64]),
         "sfem_dense_solve": (i32, [vp, i32, i32, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, sz]),
     }
     for name, (res, args) in sig.items():

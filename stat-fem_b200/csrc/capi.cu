@@ -36,6 +36,7 @@ int64_t b84_num_tiles(const B84Matrix* m);
 int rows_axpy(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, double alpha, const double* X, int64_t ldx, double* Y, int64_t ldy);
 int rows_gather(sfem_ctx* c, int64_t nrows, const int32_t* rows, int k, const double* Y, int64_t ldy, double* X, int64_t ldx);
 int mirror_lower(sfem_ctx* c, int n, double* A, int64_t ld);
+int sym_fold(sfem_ctx* c, int n, int nblocks, double* A, int64_t ld);
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev);
 int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, int k, double* B, int64_t ldb);
 int potri_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, double* W, double* Kinv);
@@ -45,6 +46,8 @@ int dense_kernel_matrix(sfem_ctx* c, int n, int d, const double* Xs, double sigm
                         int unc_vec, double rho2, const double* Cu, int which, double* M);
 size_t dense_workspace_bytes(int n);
 int dense_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z);
+int dense_skinny_gemm(sfem_ctx* c, int64_t n, int k, int ns, const double* X, int64_t ldx, const double* Cm, int64_t ldc,
+                      double* Y, int64_t ldy);
 int dense_cov_matrix(sfem_ctx* c, int m, int n, int d, const double* X1, const double* X2, double sigma, double l, int which,
                      double* M);
 int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
@@ -307,9 +310,20 @@ int sfem_mirror_lower(sfem_ctx* c, int n, double* A, int64_t lda) {
     return mirror_lower(c, n, A, lda);
 }
 
+int sfem_sym_fold(sfem_ctx* c, int n, int nblocks, double* A, int64_t lda) {
+    GUARD(c);
+    if (n < 0 || nblocks < 1 || !A) return sfem_fail(c, SFEM_ERR_ARG, "sym_fold: bad arguments");
+    return sym_fold(c, n, nblocks, A, lda);
+}
+
 int sfem_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z) {
     GUARD(c);
     return dense_axpby(c, n, a, x, b, y, z);
+}
+int sfem_skinny_gemm(sfem_ctx* c, int64_t n, int k, int ns, const double* X, int64_t ldx, const double* Cm, int64_t ldc,
+                     double* Y, int64_t ldy) {
+    GUARD(c);
+    return dense_skinny_gemm(c, n, k, ns, X, ldx, Cm, ldc, Y, ldy);
 }
 size_t sfem_dense_workspace_bytes(int n_obs) { return dense_workspace_bytes(n_obs); }
 

@@ -15,7 +15,7 @@ namespace {
 struct Scal {            // per-column scalars, each an array of k doubles
     double *rho, *alpha, *beta, *bb, *rr, *tol2;
     int* active;         // k ints
-    int* n_active;       // 1 int
+    int* n_active;       // 2 ints: [0] columns still iterating, [1] set when a norm is NaN/Inf or the true residual fails
 };
 
 // init: r = B, x = 0, partial bb = sum b^2;  JAC: z = dinv r, p = z, partial rho = sum r z
@@ -144,6 +144,7 @@ __global__ void cg_scal_init_kernel(int k, int nblk, const double* __restrict__ 
     if (atol * atol > t) t = atol * atol;
     s.tol2[c] = t;
     int act = (bb > t) ? 1 : 0;
+    if (!(fabs(bb) <= 1.7e308)) { act = 0; atomicOr(s.n_active + 1, 1); }      // NaN / Inf right-hand side: fail, never "converged"
     s.active[c] = act;
     if (part_rho) s.rho[c] = colsum(part_rho, nblk, k, c);
     if (act) atomicAdd(s.n_active, 1);
@@ -169,6 +170,7 @@ __global__ void cg_beta_kernel(int k, int nblk, const double* __restrict__ part_
     if (act) {
         double rr = colsum(part_rr, nblk, k, c);
         s.rr[c] = rr;
+        if (!(fabs(rr) <= 1.7e308)) atomicOr(s.n_active + 1, 1);               // breakdown: reported, not taken for convergence
         if (!(rr > s.tol2[c])) act = 0;
     }
     double rho_new = colsum(part_rz, nblk, k, c);
@@ -179,12 +181,18 @@ __global__ void cg_beta_kernel(int k, int nblk, const double* __restrict__ part_
     if (act) atomicAdd(s.n_active, 1);
 }
 
+// true relative residual per column; flags[1] |= 2 when it is not finite or misses the requested tolerance by more
+// than a factor RELRES_SLACK (the recurrence residual drifted from the true one)
+#define RELRES_SLACK 100.0
 __global__ void cg_relres_kernel(int k, int nblk, const double* __restrict__ part_rr, const double* __restrict__ bb,
-                                 double* __restrict__ out) {
+                                 const double* __restrict__ tol2, int* __restrict__ flags, double* __restrict__ out) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= k) return;
     double rr = colsum(part_rr, nblk, k, c);
     out[c] = bb[c] > 0.0 ? sqrt(rr / bb[c]) : sqrt(rr);
+    double lim = RELRES_SLACK * RELRES_SLACK * tol2[c];
+    if (lim < 1.e-26 * bb[c]) lim = 1.e-26 * bb[c];                           // rounding floor of an FP64 residual
+    if (!(rr <= lim)) atomicOr(flags + 1, 2);
 }
 
 // partial rr of an existing residual block
@@ -395,7 +403,7 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         else kern<1> <<<grid, RB_THREADS, 0, c->stream>>>(__VA_ARGS__);                 \
         KCHECK(c);                                                                     \
     } while (0)
-    CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, 2 * sizeof(int), c->stream));
     CUDA_TRY(c, cudaMemsetAsync(sc, 0, sizeof(double) * 8 * (size_t)kk, c->stream));
     LAUNCH_T(4, cg_init_perm_kernel, n, k, perm, B, ldb, Xq, R, Pa, part0, g.rows_per_block);
     cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, nullptr, s, rtol, atol);
@@ -406,11 +414,11 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
     KCHECK(c);
     cg_rho_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, s);
     KCHECK(c);
-    CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     int it = 0;
     int nact = *h_nact;
-    while (nact > 0 && it < max_it) {
+    while (nact > 0 && it < max_it && h_nact[1] == 0) {
         // x += alpha_prev p_prev (alpha = beta = 0 and p = 0 on the first pass), p = z + beta p
         LAUNCH_T(5, cg_pxupdate_kernel, n, k, s.alpha, s.beta, Z, Pa, Xq, g.rows_per_block);
         {   // q = A p ; sigma = p.q
@@ -433,7 +441,7 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
         cg_beta_kernel<<<sb, 128, 0, c->stream>>>(k, 1, red, red + kk, s);
         KCHECK(c);
-        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         nact = *h_nact;
         ++it;
@@ -445,14 +453,17 @@ static int cg_solve_block_tiles(sfem_ctx* c, int k, const double* B, int64_t ldb
         rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, X, ldx, R, k, B, ldb);
         if (rc) return rc;
         LAUNCH_T(1, cg_norm_kernel, n, k, R, part0, g.rows_per_block);
-        cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, relres_dev);
+        cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, s.tol2, s.n_active, relres_dev);
         KCHECK(c);
         if (relres_out_host)
             CUDA_TRY(c, cudaMemcpyAsync(relres_out_host, relres_dev, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
 #undef LAUNCH_T
+    if (h_nact[1] & 1) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: non-finite right-hand side or residual norm after %d iterations", it);
     if (nact > 0) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: %d of %d columns not converged after %d iterations", nact, k, it);
+    if (h_nact[1] & 2) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: true residual ||B - A X|| misses the tolerance by more than %gx after %d iterations (recurrence drift or indefinite operator)", RELRES_SLACK, it);
     return SFEM_OK;
 }
 
@@ -508,15 +519,15 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
         KCHECK(c);                                                                     \
     } while (0)
 
-    CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, 2 * sizeof(int), c->stream));
     LAUNCH_VJ(jac ? 4 : 3, cg_init_kernel, n, k, B, ldb, X, ldx, R, P, c->A_dinv, part0, part1, g.rows_per_block);
     cg_scal_init_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, jac ? part1 : nullptr, s, rtol, atol);
     KCHECK(c);
-    CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     int it = 0;
     int nact = *h_nact;
-    while (nact > 0 && it < max_it) {
+    while (nact > 0 && it < max_it && h_nact[1] == 0) {
         int rc = spmm_csr(c, TAG_CSR_MULT, c->A_nnz, n, c->A_ptr, c->A_idx, c->A_val, k, P, k, Q, k, part0, nullptr);
         if (rc) return rc;
         cg_alpha_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s);
@@ -525,7 +536,7 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
         CUDA_TRY(c, cudaMemsetAsync(s.n_active, 0, sizeof(int), c->stream));
         cg_beta_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part1, part2, s);
         KCHECK(c);
-        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LAUNCH_VJ(3, cg_pupdate_kernel, n, k, s.beta, jac ? R : Z, c->A_dinv, P, g.rows_per_block);
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         nact = *h_nact;
@@ -537,15 +548,18 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
         int rc = csr_residual(c, n, c->A_ptr, c->A_idx, c->A_val, k, X, ldx, R, k, B, ldb);
         if (rc) return rc;
         LAUNCH_V(1, cg_norm_kernel, n, k, R, part0, g.rows_per_block);
-        cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, relres_dev);
+        cg_relres_kernel<<<sb, 128, 0, c->stream>>>(k, g.nblk, part0, s.bb, s.tol2, s.n_active, relres_dev);
         KCHECK(c);
         if (relres_out_host) {
             CUDA_TRY(c, cudaMemcpyAsync(relres_out_host, relres_dev, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
         }
+        CUDA_TRY(c, cudaMemcpyAsync(h_nact, s.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
 #undef LAUNCH_V
 #undef LAUNCH_VJ
+    if (h_nact[1] & 1) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: non-finite right-hand side or residual norm after %d iterations", it);
     if (nact > 0) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: %d of %d columns not converged after %d iterations", nact, k, it);
+    if (h_nact[1] & 2) return sfem_fail(c, SFEM_ERR_NOT_CONVERGED, "solve_block: true residual ||B - A X|| misses the tolerance by more than %gx after %d iterations (recurrence drift or indefinite operator)", RELRES_SLACK, it);
     return SFEM_OK;
 }

@@ -173,6 +173,109 @@ int dense_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, con
     return SFEM_OK;
 }
 
+// ---- tall-skinny product  Y[n x NS] = X[n x k] C[k x NS]  (NS <= 8 right-hand columns) --------------------------------
+// Used for v = W c with the resident W = G Z (n x n_obs): A^-1 G A^-1 P c = A^-1 (W c) replaces two of the mesh-space
+// solves behind every term of the posterior mean (LinearSolver.py:283-301) by one pass over W.  HBM-bound: X is
+// streamed once (8 n k bytes); C is staged chunk-wise in shared memory, transposed so that a lane's two consecutive k
+// entries are one 16-byte load, and every staged value is reused for the four rows a warp works on.
+namespace {
+constexpr int SK_KC = 512, SK_ROWS = 4, SK_WARPS = 8;
+template <int NS, bool VEC2>
+__global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(int64_t n, int k, const double* __restrict__ X, int64_t ldx,
+                                                                   const double* __restrict__ Cm, int64_t ldc,
+                                                                   double* __restrict__ Y, int64_t ldy) {
+    __shared__ __align__(16) double cs[NS][SK_KC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ngroups = (n + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS);
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t row0 = g * (SK_WARPS * SK_ROWS) + warp * SK_ROWS;
+        double acc[SK_ROWS][NS];
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[r][s] = 0.0;
+        const double* xr[SK_ROWS];
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r) xr[r] = X + (row0 + r < n ? row0 + r : n - 1) * ldx;
+        for (int kc = 0; kc < k; kc += SK_KC) {
+            const int len = k - kc < SK_KC ? k - kc : SK_KC;
+            __syncthreads();
+            for (int t = threadIdx.x; t < SK_KC * NS; t += SK_WARPS * 32) {
+                int j = t / NS, s = t % NS;
+                cs[s][j] = j < len ? Cm[(int64_t)(kc + j) * ldc + s] : 0.0;
+            }
+            __syncthreads();
+            if (VEC2) {
+                for (int j = lane * 2; j < len; j += 64) {
+                    double2 cv[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) cv[s] = *reinterpret_cast<const double2*>(&cs[s][j]);
+#pragma unroll
+                    for (int r = 0; r < SK_ROWS; ++r) {
+                        double2 x = __ldg(reinterpret_cast<const double2*>(xr[r] + kc + j));
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) acc[r][s] = fma(x.y, cv[s].y, fma(x.x, cv[s].x, acc[r][s]));
+                    }
+                }
+            } else {
+                for (int j = lane; j < len; j += 32) {
+#pragma unroll
+                    for (int r = 0; r < SK_ROWS; ++r) {
+                        double x = __ldg(xr[r] + kc + j);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) acc[r][s] = fma(x, cs[s][j], acc[r][s]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                double v = acc[r][s];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && row0 + r < n) Y[(row0 + r) * ldy + s] = v;
+            }
+    }
+}
+
+template <int NS>
+static void skinny_launch(sfem_ctx* c, int64_t n, int k, const double* X, int64_t ldx, const double* Cm, int64_t ldc, double* Y,
+                          int64_t ldy) {
+    int64_t ngroups = (n + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS);
+    unsigned grid = (unsigned)(ngroups < 4 * SFEM_NUM_SMS ? ngroups : 4 * SFEM_NUM_SMS);
+    bool v2 = (k % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0);
+    if (v2) skinny_gemm_kernel<NS, true><<<grid, SK_WARPS * 32, 0, c->stream>>>(n, k, X, ldx, Cm, ldc, Y, ldy);
+    else skinny_gemm_kernel<NS, false><<<grid, SK_WARPS * 32, 0, c->stream>>>(n, k, X, ldx, Cm, ldc, Y, ldy);
+}
+
+}  // namespace
+
+// Y[n x ns] = X[n x k] C[k x ns] for any ns (advanced eight columns at a time)
+int dense_skinny_gemm(sfem_ctx* c, int64_t n, int k, int ns, const double* X, int64_t ldx, const double* Cm, int64_t ldc,
+                      double* Y, int64_t ldy) {
+    if (n <= 0 || ns <= 0) return SFEM_OK;
+    if (k <= 0 || !X || !Cm || !Y) return sfem_fail(c, SFEM_ERR_ARG, "skinny_gemm: bad arguments");
+    for (int s0 = 0; s0 < ns; s0 += 8) {
+        int w = ns - s0 < 8 ? ns - s0 : 8;
+        ProfScope ps(c, TAG_SPMM_OTHER, 8.0 * ((double)n * k + (double)n * w), 2.0 * (double)n * k * w);
+        const double* Cs = Cm + s0;
+        double* Ys = Y + s0;
+        switch (w) {
+            case 1: skinny_launch<1>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 2: skinny_launch<2>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 3: skinny_launch<3>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 4: skinny_launch<4>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 5: skinny_launch<5>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 6: skinny_launch<6>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            case 7: skinny_launch<7>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+            default: skinny_launch<8>(c, n, k, X, ldx, Cs, ldc, Ys, ldy); break;
+        }
+        KCHECK(c);
+    }
+    return SFEM_OK;
+}
+
 // workspace (doubles): M n^2 | W n^2 | Kinv n^2 | dinv | vectors 4n | partials | small
 size_t dense_workspace_bytes(int n) {
     size_t nn = (size_t)n * n;

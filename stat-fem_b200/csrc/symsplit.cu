@@ -103,7 +103,32 @@ __global__ void mirror_lower_tiles_kernel(int n, double* __restrict__ A, int64_t
     if (j > i) A[(int64_t)i * ld + j] = A[(int64_t)j * ld + i];
 }
 
+// Sharded symmetric assembly: the n x n array holds every unordered pair of DIFFERENT ownership blocks exactly once
+// (block (r, s) or block (s, r), the other one zero); fold it into the full symmetric matrix.  Ownership is PETSc's
+// contiguous rule (the first `extra` blocks have base + 1 entries).  Diagonal blocks are left as they are.
+__device__ __forceinline__ int owner_block(int i, int base, int extra) {
+    int cut = extra * (base + 1);
+    return i < cut ? i / (base + 1) : extra + (base > 0 ? (i - cut) / base : 0);
+}
+__global__ void sym_fold_kernel(int n, int base, int extra, double* __restrict__ A, int64_t ld) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * n) return;
+    int i = (int)(t / n), j = (int)(t % n);
+    if (j >= i || owner_block(i, base, extra) == owner_block(j, base, extra)) return;
+    double v = A[(int64_t)i * ld + j] + A[(int64_t)j * ld + i];
+    A[(int64_t)i * ld + j] = v;
+    A[(int64_t)j * ld + i] = v;
+}
+
 }  // namespace
+
+int sym_fold(sfem_ctx* c, int n, int nblocks, double* A, int64_t ld) {
+    if (n <= 0 || nblocks <= 1) return SFEM_OK;
+    ProfScope ps(c, TAG_DENSE_MISC, 16.0 * (double)n * n, 0.0);
+    sym_fold_kernel<<<(unsigned)cdiv64((int64_t)n * n, 256), 256, 0, c->stream>>>(n, n / nblocks, n % nblocks, A, ld);
+    KCHECK(c);
+    return SFEM_OK;
+}
 
 // Pass 1.  row_cnt, row_flag: device scratch of n int64 each; eptr_full, rowpos: device, n + 1 int64 each.
 int unsym_count(sfem_ctx* c, int64_t n, const int64_t* ptr, const int32_t* idx, int64_t* row_cnt, int64_t* row_flag,

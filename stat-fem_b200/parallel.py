@@ -79,6 +79,42 @@ class EnsembleComm(object):
         self._dist.recv(t, src=src, group=self.group)
         return t
 
+    def allreduce_tensor(self, t):
+        "in-place sum of a (device) tensor over the ensemble"
+        if self._dist is not None and self.size > 1:
+            self._dist.all_reduce(t, group=self.group)
+        return t
+
+    def reduce_tensor(self, t, root=0):
+        "in-place sum onto ``root`` (the other ranks' buffers are left unspecified)"
+        if self._dist is not None and self.size > 1:
+            self._dist.reduce(t, dst=root, group=self.group)
+        return t
+
+    def all_gather_into(self, out, local):
+        "out[s] = rank s's ``local`` (equal shapes; ``out`` is a persistent (size, ...) buffer owned by the caller)"
+        if self._dist is None or self.size == 1:
+            out[0].copy_(local)
+            return None
+        flat = out.view((out.shape[0] * out.shape[1],) + tuple(out.shape[2:]))       # concatenation along dim 0
+        return self._dist.all_gather_into_tensor(flat, local, group=self.group, async_op=True)
+
+    def exchange_start(self, send, dst, recv, src):
+        """post one grouped send (to ``dst``) + receive (from ``src``); either tensor may be None.  Returns the list of
+        request handles for ``exchange_finish``.  The two directions are grouped (ncclGroupStart/End under NCCL) so
+        that a ring of such calls cannot deadlock."""
+        ops = []
+        if send is not None:
+            ops.append(self._dist.P2POp(self._dist.isend, send, dst, group=self.group))
+        if recv is not None:
+            ops.append(self._dist.P2POp(self._dist.irecv, recv, src, group=self.group))
+        return self._dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def exchange_finish(reqs):
+        for q in reqs:
+            q.wait()
+
     # ---- tensor collectives used by the sharded Cu assembly -------------------------------------------------
     def all_gather_rows(self, local, counts):
         """local: tensor (m x n_loc).  Returns a list of tensors (m x counts[s]) -- every rank's column block of the
@@ -97,21 +133,34 @@ class EnsembleComm(object):
         self._dist.all_gather(outs, send, group=self.group)
         return [o[:, :int(cnt)] for o, cnt in zip(outs, counts)]
 
-    def all_gather_rows_start(self, local, counts):
-        "asynchronous all_gather_rows: returns a handle for all_gather_rows_finish (the exchange overlaps the caller's GEMM)"
+    def all_gather_rows_start(self, local, counts, buffers=None):
+        """asynchronous all_gather_rows: returns a handle for all_gather_rows_finish (the exchange overlaps the caller's
+        GEMM).  ``buffers``: a dict the caller keeps between calls; it holds the persistent receive buffer (size, m,
+        cmax) and the padded send buffer of each parity, so that the steady state allocates nothing and one
+        all_gather_into_tensor lands every rank's block in place (no per-piece copies)."""
         if self._dist is None or self.size == 1:
             return ([local], None, counts)
         import torch
         cmax = int(max(counts))
         m = int(local.shape[0])
-        if int(local.shape[1]) == cmax:
-            send = local.contiguous()
-        else:
-            send = torch.zeros((m, cmax), dtype=local.dtype, device=local.device)
+        store = buffers if buffers is not None else {}
+        slot = store.get("next", 0)
+        store["next"] = 1 - slot
+        key = ("recv", slot)
+        if key not in store or store[key].shape[1] < m or store[key].shape[2] != cmax:
+            store[key] = torch.empty((self.size, m, cmax), dtype=local.dtype, device=local.device)
+            store[("send", slot)] = torch.zeros((m, cmax), dtype=local.dtype, device=local.device)
+        recv = store[key][:, :m, :]
+        if not recv.is_contiguous():       # a shorter last chunk: use the leading part of the flat buffer instead
+            recv = store[key].view(-1)[:self.size * m * cmax].view(self.size, m, cmax)
+        if int(local.shape[1]) == cmax and local.is_contiguous():
+            send = local
+        else:       # collectives need equal shapes: pad the narrower blocks (PETSc ownership differs by at most one)
+            send = store[("send", slot)].view(-1)[:m * cmax].view(m, cmax)
             send[:, :local.shape[1]] = local
-        outs = [torch.empty((m, cmax), dtype=local.dtype, device=local.device) for _ in counts]
-        work = self._dist.all_gather(outs, send, group=self.group, async_op=True)
-        return (outs, work, counts, send)
+        # (size * m, cmax): the concatenation along dim 0, the one output layout every backend accepts
+        work = self._dist.all_gather_into_tensor(recv.view(self.size * m, cmax), send, group=self.group, async_op=True)
+        return ([recv[s] for s in range(self.size)], work, counts, send)
 
     def all_gather_rows_finish(self, handle):
         outs, work, counts = handle[0], handle[1], handle[2]

@@ -14,7 +14,7 @@ from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
 
 _KNOWN_SOLVER_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it", "pc_type", "block_size", "mg_nu", "mg_omega", "mg_omega2",
-                      "mg_max_coarse", "workspace_gb", "symmetric_split"}
+                      "mg_max_coarse", "workspace_gb", "symmetric_split", "keep_factors"}
 
 
 def _lattice_nodes(coords, bbox=None):
@@ -84,6 +84,9 @@ class SparseSolver(object):
         self.mg_omega2 = float(params.get("mg_omega2", self.mg_omega))
         self.mg_max_coarse = int(params.get("mg_max_coarse", 600))
         self.symmetric_split = bool(params.get("symmetric_split", True))
+        # keep W = G A^-1 P resident after solve_prior (8 n n_obs / ranks bytes): posterior means then cost one
+        # mesh-space solve instead of four.  None: decide from the free device memory at solve_prior time
+        self.keep_factors = params.get("keep_factors", None)
         self.n = A.shape[0]
         self.ctx = _lib.new_context()
         self._work = None
@@ -236,13 +239,15 @@ def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_by
     chunk = max(1024, min(n, int(chunk_bytes / (8. * max(n_left, 1)))))
     widths = [b - a for a, b in lcounts]
     starts = list(range(0, n, chunk))
-    # double-buffered: the all-gather of row chunk i+1 (NCCL, its own stream) is in flight while chunk i is multiplied
-    handle = ensemble_comm.all_gather_rows_start(Zl[starts[0]:min(n, starts[0] + chunk), :], widths)
+    # double-buffered: the all-gather of row chunk i+1 (NCCL, its own stream) is in flight while chunk i is multiplied;
+    # both receive buffers are allocated once and every rank's block lands in place (all_gather_into_tensor)
+    bufs = {}
+    handle = ensemble_comm.all_gather_rows_start(Zl[starts[0]:min(n, starts[0] + chunk), :], widths, bufs)
     for i, k0 in enumerate(starts):
         k1 = min(n, k0 + chunk)
         pieces = ensemble_comm.all_gather_rows_finish(handle)
         if i + 1 < len(starts):
-            handle = ensemble_comm.all_gather_rows_start(Zl[starts[i + 1]:min(n, starts[i + 1] + chunk), :], widths)
+            handle = ensemble_comm.all_gather_rows_start(Zl[starts[i + 1]:min(n, starts[i + 1] + chunk), :], widths, bufs)
         for (a, b), piece in zip(lcounts, pieces):
             if nloc and b > a:
                 gemm_tn(Wr[k0:k1], piece, res[:, a:b], 1.0)
@@ -250,10 +255,95 @@ def sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, zeros, chunk_by
     return ensemble_comm.gather_rows_to_root(res.contiguous(), [b - a for a, b in rcounts])
 
 
-def _symmetric_split_wtz(ctx, lib, G, W, Z, n, k):
+def sharded_symmetric_wtz(ensemble_comm, Ws, Z, We, Ze, n_obs, ops, chunk_bytes=1.e9):
+    """Sharded covariance assembly for the symmetric case (left and right sensors identical): Cu = (S Z)^T Z + (E Z)^T Z
+    with G = S + E as in ``_symmetric_split_wtz``.  Rank r holds ``Ws`` = S Z_r and ``Z`` = Z_r (n x its columns) and
+    the rows ``We`` = (E Z_r), ``Ze`` = Z_r at the non-empty rows of E (ne x its columns; None if E is empty).
+
+    Symmetric term, half-ring schedule: block (r, s) = Ws_r^T Z_s equals block (s, r)^T, so every unordered pair of
+    ranks is computed once -- rank r multiplies its diagonal block (tiles on and below the diagonal) and the blocks
+    (r, r+d) for ring distances d = 1 .. size/2, receiving Z_{r+d} row chunk by row chunk from rank r+d while it sends
+    its own chunks to rank r-d (double-buffered, the transfer of chunk i+1 overlaps the GEMM of chunk i).  For an even
+    size the pairs at distance size/2 are split between their two ranks (the lower rank takes the first half of its
+    own columns, the upper rank the rest), so every rank does size/2 block-GEMMs instead of the size of the plain
+    all-gather schedule.  The row blocks are gathered on rank 0 (the ``Scatter.toZero`` of solving_utils.py:146-159),
+    folded into the full symmetric matrix there (``ops.sym_fold``) and the small unsymmetric term is added.
+
+    ``ops``: the arithmetic -- gemm_tn(W, Z, out, beta), gemm_tn_lower(W, Z, out) (out = lower tiles of W^T Z,
+    mirrored), zeros(shape), empty(shape), sym_fold(T, nblocks), add(T, E) -- DMMA kernels on the GPU, torch on CPU in
+    the gloo tests.  Returns the (n_obs x n_obs) array on rank 0, None elsewhere."""
+    R, r = ensemble_comm.size, ensemble_comm.rank
+    ranges = [ownership_range(n_obs, s, R) for s in range(R)]
+    widths = [b - a for a, b in ranges]
+    lo, hi = ranges[r]
+    nloc = hi - lo
+    n = int(Ws.shape[0])
+    resS = ops.zeros((max(nloc, 1), n_obs))[:nloc]
+    if nloc:
+        ops.gemm_tn_lower(Ws, Z, resS[:, lo:hi])
+    # ---- half ring ------------------------------------------------------------------------------------------
+    cmax = max(widths)
+    chunk = max(1024, min(n, int(chunk_bytes / (8. * max(cmax, 1)))))
+    plan = [(d, k0, min(n, k0 + chunk)) for d in range(1, R // 2 + 1) for k0 in range(0, n, chunk)]
+    bufs = [ops.empty((chunk * max(cmax, 1),)) for _ in range(2)] if plan else []
+
+    def post(i):
+        d, k0, k1 = plan[i]
+        dst, src = (r - d) % R, (r + d) % R
+        send = Z[k0:k1] if (nloc and widths[dst]) else None
+        recv = bufs[i % 2][:(k1 - k0) * widths[src]].view(k1 - k0, widths[src]) if (widths[src] and nloc) else None
+        if send is not None and not send.is_contiguous():
+            send = send.contiguous()
+        return ensemble_comm.exchange_start(send, dst, recv, src), recv
+
+    pending = post(0) if plan else None
+    for i, (d, k0, k1) in enumerate(plan):
+        reqs, piece = pending
+        ensemble_comm.exchange_finish(reqs)
+        if i + 1 < len(plan):
+            pending = post(i + 1)
+        s = (r + d) % R
+        if piece is None:
+            continue
+        a, b = ranges[s]
+        if R % 2 == 0 and d == R // 2:         # the pair (r, s) meets twice at this distance: split it
+            if r < s:
+                h = nloc // 2
+                if h:
+                    ops.gemm_tn(Ws[k0:k1, :h], piece, resS[:h, a:b], 1.0)
+            else:
+                h = widths[s] // 2
+                if widths[s] - h:
+                    ops.gemm_tn(Ws[k0:k1], piece[:, h:], resS[:, a + h:b], 1.0)
+        else:
+            ops.gemm_tn(Ws[k0:k1], piece, resS[:, a:b], 1.0)
+    # ---- unsymmetric remainder: rows [lo, hi) of (E Z)^T Z -----------------------------------------------------
+    ne = 0 if We is None else int(We.shape[0])
+    resE = None
+    if ne:
+        resE = ops.zeros((max(nloc, 1), n_obs))[:nloc]
+        local = ops.zeros((ne, cmax))
+        if nloc:
+            local[:, :nloc] = Ze
+        gathered = ops.empty((R, ne, cmax))
+        work = ensemble_comm.all_gather_into(gathered, local)
+        if work is not None:
+            work.wait()
+        for s, (a, b) in enumerate(ranges):
+            if nloc and b > a:
+                ops.gemm_tn(We, gathered[s][:, :b - a], resE[:, a:b], 0.0)
+    TS = ensemble_comm.gather_rows_to_root(resS.contiguous(), widths)
+    TE = ensemble_comm.gather_rows_to_root(resE.contiguous(), widths) if ne else None
+    if r != 0:
+        return None
+    ops.sym_fold(TS, R)
+    return ops.add(TS, TE) if ne else TS
+
+
+def _symmetric_split_wtz(ctx, lib, G, W, Z, n, k, restore_W=False):
     """W^T Z for W = G Z on one process, using G = S + E (E: entries without a stored transpose, csrc/symsplit.cu):
     (S Z)^T Z is symmetric, so only the tiles on and below the diagonal are computed and mirrored; (E Z)^T Z is a GEMM
-    over the few non-empty rows of E.  W is overwritten with S Z."""
+    over the few non-empty rows of E.  W is overwritten with S Z (and put back to G Z at the end if ``restore_W``)."""
     rows, E = G.unsymmetric_part()
     ne = int(rows.shape[0])
     res = ctx.empty((k, k))
@@ -269,16 +359,73 @@ def _symmetric_split_wtz(ctx, lib, G, W, Z, n, k):
         ctx.check(lib.sfem_rows_gather(ctx.handle, ne, _lib.ptr(rows), k, _lib.ptr(Z), int(Z.stride(0)), _lib.ptr(Ze), k))
         ctx.check(lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, k, k, ne, 1.0, _lib.ptr(We), int(We.stride(0)),
                                  _lib.ptr(Ze), k, 1.0, _lib.ptr(res), k))
+        if restore_W:
+            ctx.check(lib.sfem_rows_axpy(ctx.handle, ne, _lib.ptr(rows), k, 1.0, _lib.ptr(We), int(We.stride(0)),
+                                         _lib.ptr(W), int(W.stride(0))))      # W <- S Z + E Z = G Z
     return res
 
 
-def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF, return_device=False):
+class _DeviceOps(object):
+    "the arithmetic of sharded_symmetric_wtz on the GPU (DMMA GEMMs of csrc/dgemm.cu, csrc/symsplit.cu)"
+
+    def __init__(self, ctx, lib):
+        self.ctx, self.lib = ctx, lib
+        self.zeros, self.empty = ctx.zeros, ctx.empty
+
+    def gemm_tn(self, Wb, Zb, out, beta):
+        ctx = self.ctx
+        ctx.check(self.lib.sfem_dgemm(ctx.handle, _lib.OP_T, _lib.OP_N, int(Wb.shape[1]), int(Zb.shape[1]), int(Wb.shape[0]), 1.0,
+                                      _lib.ptr(Wb), int(Wb.stride(0)), _lib.ptr(Zb), int(Zb.stride(0)), float(beta),
+                                      _lib.ptr(out), int(out.stride(0))))
+
+    def gemm_tn_lower(self, Wb, Zb, out):
+        ctx, k = self.ctx, int(Wb.shape[1])
+        ctx.check(self.lib.sfem_dgemm_lower(ctx.handle, _lib.OP_T, _lib.OP_N, k, int(Wb.shape[0]), 1.0, _lib.ptr(Wb),
+                                            int(Wb.stride(0)), _lib.ptr(Zb), int(Zb.stride(0)), 0.0, _lib.ptr(out),
+                                            int(out.stride(0))))
+        ctx.check(self.lib.sfem_mirror_lower(ctx.handle, k, _lib.ptr(out), int(out.stride(0))))
+
+    def sym_fold(self, T, nblocks):
+        ctx = self.ctx
+        ctx.check(self.lib.sfem_sym_fold(ctx.handle, int(T.shape[0]), int(nblocks), _lib.ptr(T), int(T.stride(0))))
+
+    def add(self, T, E):
+        ctx = self.ctx
+        ctx.check(self.lib.sfem_axpby(ctx.handle, T.numel(), 1.0, _lib.ptr(T), 1.0, _lib.ptr(E), _lib.ptr(T)))
+        return T
+
+
+def _sharded_symmetric_device(ensemble_comm, ctx, lib, G, W, Z, n, nloc, n_obs, restore_W=False):
+    "split W = G Z_r into S Z_r and the rows of E Z_r on this rank, then run the half-ring assembly"
+    rows, E = G.unsymmetric_part()
+    ne = int(rows.shape[0])
+    We = Ze = None
+    if ne:
+        We = ctx.zeros((ne, max(nloc, 1)))[:, :nloc]
+        Ze = ctx.zeros((ne, max(nloc, 1)))[:, :nloc]
+        if nloc:
+            E.matmul(Z, out=We)
+            ctx.check(lib.sfem_rows_axpy(ctx.handle, ne, _lib.ptr(rows), nloc, -1.0, _lib.ptr(We), int(We.stride(0)),
+                                         _lib.ptr(W), int(W.stride(0))))          # W <- S Z
+            ctx.check(lib.sfem_rows_gather(ctx.handle, ne, _lib.ptr(rows), nloc, _lib.ptr(Z), int(Z.stride(0)), _lib.ptr(Ze),
+                                           int(Ze.stride(0))))
+    full = sharded_symmetric_wtz(ensemble_comm, W, Z, We, Ze, n_obs, _DeviceOps(ctx, lib))
+    if ne and nloc and restore_W:
+        ctx.check(lib.sfem_rows_axpy(ctx.handle, ne, _lib.ptr(rows), nloc, 1.0, _lib.ptr(We), int(We.stride(0)),
+                                     _lib.ptr(W), int(W.stride(0))))              # W <- G Z again
+    return full
+
+
+def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF, return_device=False, keep=None):
     """Phi_l^T A^-1 G A^-1 Phi_r on the root process, ``(0, 0)`` elsewhere (solving_utils.py:61-169).
 
     Row i of the reference's temporary array is ``P_left^T (A^-1 G A^-1 p_i)`` and the flattened array is *reshaped*
     to ``(n_left, n_right)``; with Z = A^-1 P and W = G Z_right that array is W^T Z_left.  The sensor columns of the
     right matrix are split over ``ensemble_comm`` exactly as PETSc would (lines 117-123); each rank solves its columns,
-    all-gathers row-chunks of Z_left and accumulates its rows of W^T Z_left, which are then gathered on rank 0."""
+    all-gathers row-chunks of Z_left and accumulates its rows of W^T Z_left, which are then gathered on rank 0.
+
+    ``keep``: a dict that receives this rank's block ``W = G Z_right`` (n x its columns) and its column range
+    ``cols`` -- LinearSolver keeps it resident so that later products A^-1 G A^-1 P c are one solve of W c."""
     if not isinstance(im_left, InterpolationMatrix):
         raise TypeError("first argument to interp_covariance_to_data must be an InterpolationMatrix")
     if not isinstance(ls, SparseSolver):
@@ -322,9 +469,13 @@ def interp_covariance_to_data(im_left, G, ls, im_right, ensemble_comm=COMM_SELF,
                                  _lib.ptr(Wb), int(Wb.stride(0)), _lib.ptr(Zb), int(Zb.stride(0)), beta,
                                  _lib.ptr(out), int(out.stride(0))))
     if size == 1 and same and nloc >= 256 and ls.symmetric_split:
-        full = _symmetric_split_wtz(ctx, lib, G, Wr, Zr, n, nloc)
+        full = _symmetric_split_wtz(ctx, lib, G, Wr, Zr, n, nloc, restore_W=keep is not None)
+    elif size > 1 and same and n_right >= 256 * size and ls.symmetric_split:
+        full = _sharded_symmetric_device(ensemble_comm, ctx, lib, G, Wr, Zr, n, nloc, n_right, restore_W=keep is not None)
     else:
         full = sharded_wtz(ensemble_comm, Wr, Zl, n_left, n_right, gemm_tn, ctx.zeros)
+    if keep is not None:
+        keep["W"], keep["cols"] = Wr, (imin, imax)
     if im_left.comm.rank == 0 and rank == 0:
         out = full.reshape(-1).reshape(n_left, n_right)      # the reference's reshape (lines 164-169)
         return out if return_device else out.cpu().numpy()

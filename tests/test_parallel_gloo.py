@@ -79,6 +79,99 @@ def test_sharded_wtz(world, n, n_left, n_right):
     assert shapes == [(n_right, n_left)]
 
 
+class _TorchOps(object):
+    "CPU stand-in for the DMMA kernels driven by sharded_symmetric_wtz"
+    @staticmethod
+    def zeros(shape):
+        return torch.zeros(shape, dtype=torch.float64)
+
+    @staticmethod
+    def empty(shape):
+        return torch.full(shape, float("nan"), dtype=torch.float64)      # stale data must never be read
+
+    @staticmethod
+    def gemm_tn(Wb, Zb, out, beta):
+        out.copy_(Wb.t() @ Zb + (beta * out if beta != 0.0 else 0.0))
+
+    @staticmethod
+    def gemm_tn_lower(Wb, Zb, out):
+        full = torch.tril(Wb.t() @ Zb)                                   # lower triangle only, then mirrored
+        out.copy_(full + torch.tril(full, -1).t())
+
+    @staticmethod
+    def sym_fold(T, nblocks):
+        from stat_fem_b200.parallel import ownership_range
+        n = T.shape[0]
+        blk = np.zeros(n, dtype=np.int64)
+        for s in range(nblocks):
+            a, b = ownership_range(n, s, nblocks)
+            blk[a:b] = s
+        other = torch.from_numpy(blk[:, None] != blk[None, :])
+        T.copy_(torch.where(other, T + T.t(), T))
+
+    @staticmethod
+    def add(T, E):
+        return T + E
+
+
+def _worker_sym(rank, world, port, n, n_obs, chunk_rows, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import stat_fem_b200  # noqa: F401
+        from stat_fem_b200.parallel import EnsembleComm
+        from stat_fem_b200.solving_utils import sharded_symmetric_wtz
+        comm = EnsembleComm()
+        rng = np.random.default_rng(11)
+        S = rng.normal(size=(n, n))
+        S = torch.from_numpy(S + S.T)
+        rows = np.sort(rng.choice(n, 37, replace=False))
+        Efull = np.zeros((n, n))
+        Efull[rows] = rng.normal(size=(37, n)) * (rng.uniform(size=(37, n)) < 0.02)
+        Efull = torch.from_numpy(Efull)
+        Z = torch.from_numpy(rng.normal(size=(n, n_obs)))
+        lo, hi = comm.column_range(n_obs)
+        Zr = Z[:, lo:hi].contiguous()
+        Ws = S @ Zr
+        We = (Efull @ Zr)[rows].contiguous()
+        Ze = Zr[rows].contiguous()
+        full = sharded_symmetric_wtz(comm, Ws, Zr, We, Ze, n_obs, _TorchOps, chunk_bytes=8. * chunk_rows * max(hi - lo, 1))
+        if rank == 0:
+            ref = (((S + Efull) @ Z).t() @ Z).numpy()
+            err = float(np.max(np.abs(full.numpy() - ref)) / np.max(np.abs(ref)))
+            sym = (S @ Z).t() @ Z
+            out_q.put(("ok", err, tuple(full.shape)))
+        else:
+            assert full is None
+            out_q.put(("ok", 0.0, None))
+    except Exception as exc:     # pragma: no cover - reported to the parent
+        import traceback
+        out_q.put(("fail", traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,n_obs,chunk_rows", [(2, 1300, 9, 1024), (2, 1100, 8, 4000), (3, 1200, 10, 1024), (4, 1250, 13, 1024),
+                                                      (4, 1100, 3, 4000), (5, 1100, 11, 1024)])
+def test_sharded_symmetric_half_ring(world, n, n_obs, chunk_rows):
+    """the half-ring schedule of the symmetric covariance assembly: even and odd world sizes (the split pair at distance
+    size/2), uneven ownership, several row chunks per ring step, ranks without columns"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sym, args=(r, world, port, n, n_obs, chunk_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for status, val, shape in results:
+        assert status == "ok", val
+        assert val < 1e-12
+    assert [s for _, _, s in results if s is not None] == [(n_obs, n_obs)]
+
+
 def test_ownership_ranges_match_petsc_rule():
     from stat_fem_b200.parallel import ownership_range
     for n in (0, 1, 7, 100, 4096):
