@@ -175,7 +175,7 @@ def test_estimate_params_MAP(case):
           "evals", ls.n_logpost_evals)
     assert abs(lp - float(c["map_logpost"])) <= TOL_LP * max(1., abs(float(c["map_logpost"])))
     if kw:     # tight tolerances: the optimum itself is pinned
-        assert_allclose(ls.params, c["map_params"], rtol=1e-4, atol=1e-4)
+        assert_allclose(ls.params, c["map_params"], rtol=TOL_LP, atol=TOL_LP)
     # seeded random start (test_estimation.py:27-35) runs and succeeds
     np.random.seed(234)
     ls2 = stat_fem.estimate_params_MAP(A, b, G, od)
