@@ -10,7 +10,8 @@ import numpy as np
 from scipy.linalg import LinAlgError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstatfem_b200.so")
+# SFEM_LIB_PATH: a diagnostic build of the same library (e.g. with -DSFEM_PANEL_CLOCKS, tools/panel_clocks.py)
+LIB_PATH = os.environ.get("SFEM_LIB_PATH") or os.path.join(_HERE, "libstatfem_b200.so")
 
 SFEM_ERR_CUDA, SFEM_ERR_ARG, SFEM_ERR_NOT_SPD, SFEM_ERR_NOT_CONVERGED, SFEM_ERR_STATE, SFEM_ERR_LIMIT = -1, -2, -3, -4, -5, -6
 OP_N, OP_T = 0, 1

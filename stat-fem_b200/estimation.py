@@ -45,13 +45,22 @@ def fit_linear_solver(ls, start=None, **minimize_kwargs):
     return ls
 
 
-def fit_snapshots(ls, datas, start=None, concurrent=True, **minimize_kwargs):
+def fit_snapshots(ls, datas, start=None, concurrent=True, polish=False, accept_precision_floor=False, **minimize_kwargs):
     """MAP fits for several data snapshots taken at the SAME sensors: the prior (x, mu, Cu) of ``ls`` is shared
     (``LinearSolver.clone_for_data``).  On one process every snapshot's L-BFGS-B loop runs in its own host thread on its
     own CUDA stream, so that the latency-bound parts of one fit (Cholesky panels, small GEMMs) overlap with the
     throughput-bound parts of the others.  On several processes (one per GPU) the prior is first broadcast to every
     GPU (``share_prior``) and the snapshots are dealt out round-robin; the optima are exchanged at the end, so every
-    process returns the same list of fitted LinearSolvers.  Extension over the reference API."""
+    process returns the same list of fitted LinearSolvers.  Extension over the reference API.
+
+    ``accept_precision_floor``: with tolerances below what FP64 can resolve at a few thousand sensors (the objective
+    carries a relative rounding noise of ~1e-13; estimation.py:92-93 forwards e.g. ftol=1e-15) L-BFGS-B ends in
+    "ABNORMAL_TERMINATION_IN_LNSRCH" -- no lower function value can be *measured* any more -- and the reference's
+    ``assert success`` (estimation.py:95) would fire.  With this flag that termination is accepted as converged.
+    ``polish``: afterwards refine the optimum with a few chord-Newton steps on the ANALYTIC gradient (Hessian by
+    central differences of ``logpost_deriv``): the gradient is resolved far below the noise of the function values, so
+    the optimum becomes reproducible to ~1e-8 -- independent of the summation order in which Cu was assembled (one
+    GPU or several).  ``minimize_result`` of every solver records what happened."""
     import threading
     import torch
     if ls.Cu is None or ls.mu is None:
@@ -78,10 +87,10 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, **minimize_kwargs):
         try:
             if use_stream:
                 with torch.cuda.stream(solvers[i].dctx.tstream):
-                    _minimize_local(solvers[i], start, minimize_kwargs)
+                    _minimize_local(solvers[i], start, minimize_kwargs, polish, accept_precision_floor)
                     solvers[i].dctx.sync()
             else:
-                _minimize_local(solvers[i], start, minimize_kwargs)
+                _minimize_local(solvers[i], start, minimize_kwargs, polish, accept_precision_floor)
             results[i, :3] = solvers[i].params
             results[i, 3] = solvers[i].n_logpost_evals
         except BaseException as exc:      # re-raised in the caller
@@ -111,13 +120,49 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, **minimize_kwargs):
     return solvers
 
 
-def _minimize_local(ls, start, minimize_kwargs):
+def newton_polish(ls, theta, step=1.e-3, max_iter=6, tol=1.e-9):
+    """Chord-Newton refinement of a stationary point of the negative log posterior using only its analytic gradient:
+    H = central differences of ``logpost_deriv`` (6 evaluations), then theta <- theta - H^-1 g until the update is
+    below ``tol``.  Returns (theta, info); theta is returned unchanged if H is not positive definite or the iteration
+    does not contract (then the L-BFGS-B point was not near a minimum)."""
+    theta = np.array(theta, dtype=np.float64)
+    H = np.zeros((3, 3))
+    for k in range(3):
+        e = np.zeros(3)
+        e[k] = step
+        H[:, k] = (ls.logpost_deriv(theta + e) - ls.logpost_deriv(theta - e)) / (2. * step)
+    H = 0.5 * (H + H.T)
+    info = dict(hessian=H, iterations=0, converged=False, last_update=None)
+    if not np.all(np.linalg.eigvalsh(H) > 0.):
+        return theta, info
+    x = theta.copy()
+    prev = np.inf
+    for it in range(max_iter):
+        dx = np.linalg.solve(H, ls.logpost_deriv(x))
+        size = float(np.max(np.abs(dx)))
+        if not np.isfinite(size) or size > 0.1 or size > 2. * prev:
+            return theta, info                    # not contracting: keep the optimiser's point
+        x = x - dx
+        prev = size
+        info.update(iterations=it + 1, last_update=size)
+        if size < tol:
+            info["converged"] = True
+            break
+    return x, info
+
+
+def _minimize_local(ls, start, minimize_kwargs, polish=False, accept_precision_floor=False):
     "the L-BFGS-B loop of fit_linear_solver without its cross-process checks (used per snapshot / per thread)"
     ls.fuse_gradient = True
     try:
         fmin_dict = minimize(ls.logposterior, start, method='L-BFGS-B', jac=ls.logpost_deriv, options=minimize_kwargs)
+        at_floor = accept_precision_floor and "ABNORMAL" in str(fmin_dict['message']).upper()
+        assert fmin_dict['success'] or at_floor, "minimization routine failed: %s" % (fmin_dict['message'],)
+        x = fmin_dict['x']
+        if polish:
+            x, info = newton_polish(ls, x)
+            fmin_dict['polish'] = info
     finally:
         ls.fuse_gradient = False
-    assert fmin_dict['success'], "minimization routine failed"
-    ls.set_params(fmin_dict['x'])
+    ls.set_params(x)
     ls.minimize_result = fmin_dict

@@ -1,7 +1,8 @@
 """Phase timing of the Cholesky panel kernel (clock64 stamps).  Needs a library built with the stamps enabled:
     make -C stat-fem_b200/csrc clean && make -C stat-fem_b200/csrc NVCC_EXTRA=-DSFEM_PANEL_CLOCKS"""
 import sys, ctypes as C
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import stat_fem_b200
 from stat_fem_b200 import _lib
