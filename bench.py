@@ -241,7 +241,8 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     import stat_fem_b200 as stat_fem
     from stat_fem_b200 import _lib
     comm = stat_fem.EnsembleComm() if world > 1 else stat_fem.COMM_SELF
@@ -416,6 +417,7 @@ def _parity_capture(prob, r):
     "host copies of what the checker compares (taken from the last resident step on rank 0)"
     ls, G = r["ls"], r["G"]
     ls.host_results = True
+    ls._local_eval = True           # rank 0 alone evaluates here: no per-evaluation broadcast (it would wait for the other ranks)
     cap = dict(mu=np.asarray(ls.mu), Cu=ls._Cu_dev.cpu().numpy(), G=G.G.to_host(), P=ls.im.interp)
     dense = {}
     if prob["nobs"] <= 16384:

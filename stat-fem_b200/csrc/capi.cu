@@ -115,6 +115,7 @@ int sfem_destroy(sfem_ctx* c) {
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+    if (c->ev_head) cudaEventDestroy(c->ev_head);
     if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
     return SFEM_OK;

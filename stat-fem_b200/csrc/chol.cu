@@ -5,6 +5,7 @@
 // DMMA GEMMs (dgemm.cu), as are the block forward/backward substitutions of potrs and the two triangular products
 // of potri.  Replaces SciPy/LAPACK cho_factor / cho_solve at LinearSolver.py:273-297, 353-367, 603-607, 662-677.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -286,7 +287,7 @@ static void* dense_tmp(sfem_ctx* c, size_t bytes) {
 // K = 512, where the DMMA GEMM runs at full pipeline efficiency (a K = 128 update is mostly pipeline fill and C
 // traffic).  The panel solve writes to a temporary (so it may use small tiles and fill the machine) and the copy back
 // into A is off the critical path.
-int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
+static int potrf_lower_blocked(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
     constexpr int NB2 = 512;
     CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
     size_t dyn = sizeof(double) * (NB * PLD + 4 * SB * DLD + NB);
@@ -372,6 +373,99 @@ int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* i
     c->dgemm_tag = TAG_DGEMM;
     if (aux_busy) CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
     return rc;
+}
+
+// Pipelined right-looking factorisation (default).  The chain of dependent 128x128 diagonal blocks is what bounds a
+// single factorisation at n_obs = 4096 (32 panels; the trailing updates total only n^3/3 = 2.3e10 flop), so the
+// critical path is kept as short as the data dependence allows and everything else runs beside it:
+//   main stream:  P(j) [factor block j, Dinv_j]  ->  head(j): the ONE block row the next panel needs,
+//                 Th = A[j+1, j] Dinv_j^T,  A[j+1, j+1] -= Th Th^T  ->  P(j+1) ...
+//   side stream:  TRSM(j): T = A[j+1.., j] Dinv_j^T for all rows; SYRK(j): A[j+2.., j+1..] -= T T^T (lower tiles, every
+//                 block row except the head's); copy T back over A[j+1.., j] once the head has consumed the raw block.
+// head(j) waits for SYRK(j-1) (its inputs carry the updates of all earlier panels); TRSM(j) waits for P(j).  Per panel
+// the main stream executes three small kernels while the side stream streams the O(m^2) update of the previous panel.
+static int potrf_lower_pipelined(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
+    CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
+    size_t dyn = sizeof(double) * (NB * PLD + 4 * SB * DLD + NB);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        attr_set = true;
+    }
+    double* T = (double*)dense_tmp(c, sizeof(double) * ((size_t)n * NB + (size_t)NB * NB));
+    if (!T) return sfem_fail(c, SFEM_ERR_CUDA, "potrf: temporary allocation failed");
+    double* TH = T + (size_t)n * NB;                       // head block (<= 128 x 128)
+    if (!c->aux_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
+    }
+    if (!c->ev_head) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_head, cudaEventDisableTiming));
+    cudaStream_t main_stream = c->stream, side = c->aux_stream;
+    // the side stream starts behind everything already queued on the main stream (the matrix itself)
+    CUDA_TRY(c, cudaEventRecord(c->ev_main, main_stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(side, c->ev_main, 0));
+    int rc = SFEM_OK;
+    bool side_used = false;
+    for (int j0 = 0; j0 < n && rc == SFEM_OK; j0 += NB) {
+        const int nb = imin(NB, n - j0);
+        double* Ajj = A + (int64_t)j0 * lda + j0;
+        double* Dj = dinv + (size_t)(j0 / NB) * NB * NB;
+        {
+            ProfScope ps(c, TAG_POTRF_PANEL, 24.0 * nb * nb, (2.0 / 3.0) * nb * nb * nb);
+            potrf_panel_kernel<<<1, 256, dyn, main_stream>>>(Ajj, lda, nb, j0, Dj, info_dev);
+            KCHECK(c);
+        }
+        const int m = n - j0 - nb;
+        if (m <= 0) break;
+        CUDA_TRY(c, cudaEventRecord(c->ev_main, main_stream));              // P(j) done: Dinv_j is ready
+        const int j1 = j0 + nb, nbn = imin(NB, m);
+        double* A21 = A + (int64_t)j1 * lda + j0;
+        double* A22 = A + (int64_t)j1 * lda + j1;
+        // ---- main: head(j)
+        if (side_used) CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));     // SYRK(j-1) has updated the inputs
+        c->dgemm_tag = TAG_CHOL_TRSM;
+        rc = dgemm(c, OP_N, OP_T, nbn, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, TH, NB, 0);
+        c->dgemm_tag = TAG_CHOL_SYRK;
+        if (rc == SFEM_OK) rc = dgemm(c, OP_N, OP_T, nbn, nbn, nb, -1.0, TH, NB, TH, NB, 1.0, A22, lda, 1);
+        if (rc) break;
+        CUDA_TRY(c, cudaEventRecord(c->ev_head, main_stream));              // raw A[j+1, j] consumed
+        // ---- side: TRSM(j), SYRK(j) below the head row, copy-back
+        c->stream = side;
+        CUDA_TRY(c, cudaStreamWaitEvent(side, c->ev_main, 0));
+        c->dgemm_tag = TAG_CHOL_TRSM;
+        rc = dgemm(c, OP_N, OP_T, m, nb, nb, 1.0, A21, lda, Dj, NB, 0.0, T, NB, 0);
+        c->dgemm_tag = TAG_CHOL_SYRK;
+        if (rc == SFEM_OK && m > nbn)
+            rc = dgemm(c, OP_N, OP_T, m - nbn, m, nb, -1.0, T + (size_t)nbn * NB, NB, T, NB, 1.0, A22 + (int64_t)nbn * lda, lda,
+                       1 | (nbn << 8));
+        if (rc == SFEM_OK) {
+            cudaEventRecord(c->ev_aux, side);                                // SYRK(j) done
+            cudaStreamWaitEvent(side, c->ev_head, 0);
+            cudaMemcpy2DAsync(A21, sizeof(double) * lda, T, sizeof(double) * NB, sizeof(double) * nb, m,
+                              cudaMemcpyDeviceToDevice, side);
+            side_used = true;
+        }
+        c->stream = main_stream;
+        c->dgemm_tag = TAG_DGEMM;
+    }
+    c->stream = main_stream;
+    c->dgemm_tag = TAG_DGEMM;
+    if (side_used) {
+        cudaEventRecord(c->ev_aux, side);
+        CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_aux, 0));
+    }
+    return rc;
+}
+
+int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
+    static int mode = -1;       // SFEM_POTRF=blocked selects the two-level blocked variant (A/B timing)
+    if (mode < 0) {
+        const char* e = getenv("SFEM_POTRF");
+        mode = (e && e[0] == 'b') ? 1 : 0;
+    }
+    if (mode == 1 || n <= 2 * NB) return potrf_lower_blocked(c, n, A, lda, dinv, info_dev);
+    return potrf_lower_pipelined(c, n, A, lda, dinv, info_dev);
 }
 
 // B (n x k, ldb) <- inv(L L^T) B.  ncols_tri > 0 limits the forward pass to a lower-trapezoidal RHS (potri).

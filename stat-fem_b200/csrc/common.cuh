@@ -73,7 +73,7 @@ struct sfem_ctx {
     void* pinned = nullptr;          // small pinned host buffer for scalar read-backs
     void* dense_tmp = nullptr; size_t dense_tmp_bytes = 0;   // panel / trtri temporaries of chol.cu (owned, grows)
     cudaStream_t aux_stream = nullptr;                        // look-ahead stream of the blocked Cholesky (owned, lazy)
-    cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_head = nullptr;
 };
 
 int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);

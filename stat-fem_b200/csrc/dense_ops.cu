@@ -395,16 +395,21 @@ int dense_posterior_cov(sfem_ctx* c, int n, int d, const double* Xs, const doubl
     rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
     if (rc) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(&info2, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    // muy -= rho^2 Cu (LC^-1 muy)
-    CUDA_TRY(c, cudaMemcpyAsync(t2, muy, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    rc = potrs_lower(c, n, w.M, n, w.dinv, 1, t2, 1);
+    // inv(LC LC^T) explicitly (trtri by recursive doubling + inv(L)^T inv(L): n^3 flop in large GEMMs) instead of a block
+    // substitution with n right-hand sides, whose n/128 dependent rank-128 updates run at half the GEMM rate
+    rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
     if (rc) return rc;
+    // muy -= rho^2 Cu (LC^-1 muy)
+    {
+        ProfScope ps(c, TAG_DENSE_MISC, 8.0 * (double)n * n, 2.0 * (double)n * n);
+        gemv_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(n, w.Kinv, muy, t2);
+        KCHECK(c);
+    }
     rc = dgemm(c, OP_N, OP_N, n, 1, n, -rho * rho, Cu, n, t2, 1, 1.0, muy, 1, 0);
     if (rc) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(muy_out, muy, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     // Cuy = Cu - rho^2 Cu (LC^-1 Cu)
-    CUDA_TRY(c, cudaMemcpyAsync(w.W, Cu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c->stream));
-    rc = potrs_lower(c, n, w.M, n, w.dinv, n, w.W, n);
+    rc = dgemm(c, OP_N, OP_N, n, n, n, 1.0, w.Kinv, n, Cu, n, 0.0, w.W, n, 0);
     if (rc) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(Cuy_out, Cu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, c->stream));
     rc = dgemm(c, OP_N, OP_N, n, n, n, -rho * rho, Cu, n, w.W, n, 1.0, Cuy_out, n, 0);

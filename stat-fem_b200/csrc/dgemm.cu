@@ -36,6 +36,7 @@ struct GemmParams {
     double* C; int64_t ldc;
     double alpha, beta;
     int lower_only;      // skip tiles strictly above the block diagonal
+    int diag_off;        // ... of a C whose row 0 sits diag_off rows below its column 0 (tiles with n0 > m0 + diag_off are skipped)
     int tri_k;           // 1: k starts at max(m0, n0) (both operands lower-triangular "k >= index")
     int64_t kchunk;      // split-K chunk (multiple of BK); gridDim.z chunks
     double* partial;     // split-K workspace [gridDim.z][M][N] or nullptr
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, (TB == 128 ? 1 : 2)) dgemm_kernel(Ge
     int tm = first_m + (tile % tiles_per_group) % gsize;
     int tn = (tile % tiles_per_group) / gsize;
     int m0 = tm * BM, n0 = tn * BN;
-    if (p.lower_only && n0 > m0) return;
+    if (p.lower_only && n0 > m0 + p.diag_off) return;
     p.A += (int64_t)blockIdx.y * p.bsA;
     p.B += (int64_t)blockIdx.y * p.bsB;
     p.C += (int64_t)blockIdx.y * p.bsC;
@@ -235,11 +236,11 @@ __global__ void __launch_bounds__(NTHREADS, (TB == 128 ? 1 : 2)) dgemm_kernel(Ge
 }
 
 __global__ void splitk_reduce_kernel(int M, int N, int splits, const double* __restrict__ partial, double alpha,
-                                     double beta, double* __restrict__ C, int64_t ldc, int lower_only, int tb) {
+                                     double beta, double* __restrict__ C, int64_t ldc, int lower_only, int tb, int diag_off) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * N) return;
     int m = (int)(idx / N), n = (int)(idx % N);
-    if (lower_only && (n / tb) > (m / tb)) return;
+    if (lower_only && (n / tb) * tb > (m / tb) * tb + diag_off) return;
     double s = 0.0;
     for (int z = 0; z < splits; ++z) s += partial[(size_t)z * M * N + idx];
     double* c = C + (int64_t)m * ldc + n;
@@ -276,6 +277,7 @@ int launch_layout(sfem_ctx* c, const GemmParams& p, bool al16, dim3 grid, bool a
 // tri: 0 none, 1 = k starts at max(m0,n0) (used for Linv^T Linv).  Encoded in the high bits of lower_only:
 //   lower_only & 1 -> only tiles on/below the block diagonal, lower_only & 2 -> tri_k.
 //   lower_only & 4 -> C aliases an operand: keep 128-tiles;  & 8 -> k starts at n0;  & 16 -> k ends at m0 + tile.
+//   bits 8.. (flags >> 8): diag_off in elements for the lower-only test (C's first row is that many rows below the diagonal).
 int dgemm(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
     return dgemm_batched(c, opA, opB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0);
@@ -290,6 +292,7 @@ int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
     p.alpha = alpha; p.beta = beta;
     p.lower_only = flags & 1;
+    p.diag_off = flags >> 8;
     p.tri_k = (flags & 2) ? 1 : 0;
     p.k_from_n0 = (flags & 8) ? 1 : 0;
     p.k_to_m0 = (flags & 16) ? 1 : 0;
@@ -335,7 +338,7 @@ int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double
     if (splits > 1) {
         int64_t tot = (int64_t)M * N;
         splitk_reduce_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, c->stream>>>(M, N, splits, p.partial, alpha, beta,
-                                                                               C, ldc, p.lower_only, tb);
+                                                                               C, ldc, p.lower_only, tb, p.diag_off);
         KCHECK(c);
     }
     return SFEM_OK;
