@@ -459,12 +459,17 @@ static int potrf_lower_pipelined(sfem_ctx* c, int n, double* A, int64_t lda, dou
 }
 
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
-    static int mode = -1;       // SFEM_POTRF=blocked selects the two-level blocked variant (A/B timing)
+    // Default: the two-level blocked variant.  Measured on B200 (profiles/r02_potrf_ab.md): the pipelined variant is 3 %
+    // faster for ONE factorisation at n = 4096 (6.59 vs 6.82 ms per value+gradient evaluation) but slower at n = 8192
+    // (31.9 vs 28.9 ms) and slower when eight fits share the GPU (5.1 vs 4.0 ms per evaluation): the panel kernel is a
+    // latency chain, and the GEMMs running beside it pull the SM clock down (1965 -> ~1400 MHz under tensor load), which
+    // lengthens the chain by as much as the overlap saves.  SFEM_POTRF=pipelined selects it.
+    static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("SFEM_POTRF");
-        mode = (e && e[0] == 'b') ? 1 : 0;
+        mode = (e && e[0] == 'p') ? 1 : 0;
     }
-    if (mode == 1 || n <= 2 * NB) return potrf_lower_blocked(c, n, A, lda, dinv, info_dev);
+    if (mode == 0 || n <= 2 * NB) return potrf_lower_blocked(c, n, A, lda, dinv, info_dev);
     return potrf_lower_pipelined(c, n, A, lda, dinv, info_dev);
 }
 
