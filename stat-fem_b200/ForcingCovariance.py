@@ -8,6 +8,7 @@ import ctypes as C
 import numpy as np
 from . import _lib
 from . import fem
+from . import adapter
 from .covariance_functions import sqexp
 
 _BORDER_CAP = 4096
@@ -15,8 +16,8 @@ _BORDER_CAP = 4096
 
 class ForcingCovariance(object):
     def __init__(self, function_space, sigma, l, cutoff=1.e-3, regularization=1.e-8, cov=sqexp):
-        if not isinstance(function_space, fem.P1Space):
-            raise TypeError("bad input type for function_space: must be a FunctionSpace")
+        # native P1Space, or any duck-typed P1 function space (Firedrake WithGeometry): see adapter.py
+        function_space = adapter.as_function_space(function_space)
         self.function_space = function_space
         self.comm = function_space.comm
         self.nx = function_space.dim()
@@ -69,8 +70,7 @@ class ForcingCovariance(object):
         if self.is_assembled:
             return
         if self.cov is not sqexp:
-            raise NotImplementedError("only the squared-exponential covariance is implemented on the GPU; "
-                                      "there is no CPU path for user-supplied covariance callables")
+            return self._assemble_callable()
         ctx = _lib.get_context()
         lib = _lib.lib()
         coords = np.ascontiguousarray(self.function_space.coords, dtype=np.float64)
@@ -78,13 +78,16 @@ class ForcingCovariance(object):
         int_basis = self._integrate_basis_functions()
         R = self._search_radius(int_basis)
         lo, hi = self.function_space.bounding_box()
+        ext = float((hi - lo).max())
+        # the cell list holds at most 2^28 cells and 4096 per direction (csrc/gcov.cu); a cell edge LARGER than the search
+        # radius is always valid (the 3^d neighbourhood still covers it), so small radii just get coarser cells
+        min_edge = ext / float(min(4000, int(2. ** (28. / d)) - 2)) if ext > 0. else 1.
         if R < 0.:
-            cell_edge = float(max((hi - lo).max(), 1.) * 1.e-3)      # diagonal only: any small cell will do
-            cell_edge = max(cell_edge, float((hi - lo).max()) / 2048.)
+            cell_edge = max(min_edge, ext / 2048., 1.e-300)            # diagonal only: any small cell will do
+        elif R > 0.:
+            cell_edge = max(R, min_edge)
         else:
-            cell_edge = R
-            if R > 0. and float((hi - lo).max()) / R >= 4000.:
-                raise ValueError("cutoff radius is too small relative to the domain for the cell list")
+            cell_edge = 0.                                             # cutoff <= 0: all pairs
         d_coords = _lib.cached_upload(self.function_space, "coords", ctx, lambda: ctx.to_device(coords, np.float64))
         d_b = _lib.cached_upload(self.function_space, "int_basis", ctx, lambda: ctx.to_device(int_basis, np.float64))
         import torch
@@ -93,11 +96,18 @@ class ForcingCovariance(object):
         nnz, maxnnz, nborder = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         lo3 = (C.c_double * 3)(*(list(lo) + [0.] * (3 - d)))
         hi3 = (C.c_double * 3)(*(list(hi) + [0.] * (3 - d)))
-        ctx.check(lib.sfem_gcov_count(ctx.handle, n, d, _lib.ptr(d_coords), _lib.ptr(d_b),
-                                      float(np.exp(2. * self.sigma)), float(np.exp(-2. * self.l)), float(self.cutoff),
-                                      float(self.regularization), float(int_basis.max()), float(cell_edge), lo3, hi3,
-                                      _lib.ptr(d_indptr), C.byref(nnz), C.byref(maxnnz), _lib.ptr(d_border),
-                                      _BORDER_CAP, C.byref(nborder)))
+        def count(edge):
+            return lib.sfem_gcov_count(ctx.handle, n, d, _lib.ptr(d_coords), _lib.ptr(d_b),
+                                       float(np.exp(2. * self.sigma)), float(np.exp(-2. * self.l)), float(self.cutoff),
+                                       float(self.regularization), float(int_basis.max()), float(edge), lo3, hi3,
+                                       _lib.ptr(d_indptr), C.byref(nnz), C.byref(maxnnz), _lib.ptr(d_border),
+                                       _BORDER_CAP, C.byref(nborder))
+        rc = count(cell_edge)
+        if rc == _lib.SFEM_ERR_LIMIT and cell_edge > 0.:
+            # a row keeps more entries than the cell-list kernels sort in shared memory (long correlation length on a
+            # fine mesh): the all-pairs mode has no such cap (rows are visited in ascending column order)
+            rc = count(0.)
+        ctx.check(rc)
         d_indices = ctx.empty((max(nnz.value, 1),), torch.int32)
         d_vals = ctx.empty((max(nnz.value, 1),), torch.float64)
         ctx.check(lib.sfem_gcov_fill(ctx.handle, _lib.ptr(d_indptr), _lib.ptr(d_indices), _lib.ptr(d_vals)))
@@ -108,6 +118,63 @@ class ForcingCovariance(object):
             d_indptr, d_indices, d_vals = self._redecide(ctx, d_indptr, d_indices, d_vals, d_border, coords, int_basis)
         self.G = _lib.DeviceCSR(ctx, (n, n), d_indptr, d_indices, d_vals, on_device=True)
         self.is_assembled = True
+
+    def _assemble_callable(self, chunk_entries=2.e7):
+        """G for a user-supplied covariance callable ``cov(x1, x2, sigma, l) -> (len(x1), len(x2))`` (the ``cov=``
+        argument of ForcingCovariance.py:52-53, used at line 161).  A Python callable can only be evaluated on the host:
+        the reference's row rule (ForcingCovariance.py:159-167) is applied here to blocks of rows at a time with NumPy,
+        in the reference's operation order, and the resulting CSR (int32 ascending columns) is uploaded.  Everything
+        downstream of G (G x, W = G Z, Cu) runs on the GPU as for the built-in kernel; only ``sqexp`` has a device
+        assembly kernel (csrc/gcov.cu)."""
+        ctx = _lib.get_context()
+        coords = np.ascontiguousarray(self.function_space.coords, dtype=np.float64)
+        n = coords.shape[0]
+        b = self._integrate_basis_functions()
+        rows_per = int(max(1, min(n, chunk_entries // max(n, 1))))
+        ptr = np.zeros(n + 1, dtype=np.int64)
+        idx_parts, val_parts = [], []
+        maxnnz = 0
+        for r0 in range(0, n, rows_per):
+            r1 = min(n, r0 + rows_per)
+            K = np.asarray(self.cov(coords[r0:r1], coords, self.sigma, self.l), dtype=np.float64)
+            assert K.shape == (r1 - r0, n), "cov must return an array of shape (len(x1), len(x2))"
+            row = (b[r0:r1, None] * b[None, :]) * K
+            ar = np.arange(r1 - r0)
+            row[ar, r0 + ar] += self.regularization
+            keep = (row / row[ar, r0 + ar][:, None]) > self.cutoff
+            cnt = keep.sum(axis=1)
+            ptr[r0 + 1:r1 + 1] = cnt
+            maxnnz = max(maxnnz, int(cnt.max()))
+            rr, cc = np.nonzero(keep)            # row-major: ascending columns inside every row
+            idx_parts.append(cc.astype(np.int32))
+            val_parts.append(row[rr, cc])
+        np.cumsum(ptr, out=ptr)
+        self.max_row_nnz = maxnnz
+        self.n_borderline = 0
+        self.G = _lib.DeviceCSR(ctx, (n, n), ptr, np.concatenate(idx_parts), np.concatenate(val_parts))
+        self.is_assembled = True
+
+    # ---- persistence (SURVEY 8f rank 4): the assembled matrix with the parameters that produced it -------------
+    def save(self, path):
+        "write the assembled G (CSR) and its parameters to ``path`` (.npz)"
+        if not self.is_assembled:
+            self.assemble()
+        ip, ix, v = self.G.to_host()
+        np.savez(path, indptr=ip, indices=ix, data=v, sigma=self.sigma, l=self.l, cutoff=self.cutoff,
+                 regularization=self.regularization, nx=self.nx, max_row_nnz=self.max_row_nnz,
+                 cov=getattr(self.cov, "__name__", "callable"))
+
+    @classmethod
+    def load(cls, function_space, path, cov=sqexp):
+        "a ForcingCovariance over ``function_space`` with G read back from ``save`` (no re-assembly)"
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        G = cls(function_space, float(z["sigma"]), float(z["l"]), float(z["cutoff"]), float(z["regularization"]), cov)
+        assert int(z["nx"]) == G.nx, "the saved matrix belongs to a function space of another size"
+        ctx = _lib.get_context()
+        G.G = _lib.DeviceCSR(ctx, (G.nx, G.nx), z["indptr"], z["indices"], z["data"])
+        G.max_row_nnz = int(z["max_row_nnz"])
+        G.is_assembled = True
+        return G
 
     def unsymmetric_part(self):
         """(rows, E) with E the compact-row device CSR of the entries of G whose transpose is not stored, and ``rows``
@@ -177,12 +244,12 @@ class ForcingCovariance(object):
 
     def mult(self, x, y):
         "y <- G x for mesh-space vectors (ForcingCovariance.py:212-242)"
-        assert isinstance(x, fem.Vector), "x must be a firedrake vector"
-        assert isinstance(y, fem.Vector), "y must be a firedrake vector"
+        assert adapter.is_vector_like(x), "x must be a firedrake vector"
+        assert adapter.is_vector_like(y), "y must be a firedrake vector"
         if not self.is_assembled:
             self.assemble()
         ctx = self.G.ctx
-        dx = ctx.to_device(x.array, np.float64)
+        dx = ctx.to_device(adapter.function_array(x), np.float64)
         y.set_local(self.G.matmul(dx).cpu().numpy())
 
     def get_nx(self):

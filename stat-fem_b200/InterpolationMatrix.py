@@ -6,6 +6,7 @@ import numpy as np
 import scipy.sparse as sp
 from . import _lib
 from . import fem
+from . import adapter
 
 
 def interpolate_cell(data_coord, nodal_points):
@@ -25,8 +26,7 @@ def interpolate_cell(data_coord, nodal_points):
 
 class InterpolationMatrix(object):
     def __init__(self, function_space, coords):
-        if not isinstance(function_space, fem.P1Space):
-            raise TypeError("bad input type for function_space: must be a FunctionSpace")
+        function_space = adapter.as_function_space(function_space)
         self.coords = np.copy(coords)
         self.function_space = function_space
         self.comm = function_space.comm
@@ -64,10 +64,12 @@ class InterpolationMatrix(object):
         self.is_assembled = True
 
     def _gather(self):
-        pass    # single spatial process: the data-space vector already lives on the root
+        """InterpolationMatrix.py:136-148 gathers the distributed data-space PETSc Vec on rank 0.  Here every process
+        holds the whole mesh (the parallel axis is the ensemble of sensor columns, not the mesh), so the data-space
+        vector already lives where it is needed: nothing to move."""
 
     def _scatter(self):
-        pass
+        "InterpolationMatrix.py:150-162 (root -> distributed data-space Vec): nothing to move, see _gather"
 
     def destroy(self):
         self.interp = self.csc = self.csr = None
@@ -89,12 +91,12 @@ class InterpolationMatrix(object):
         "P^T v as a NumPy array (InterpolationMatrix.py:223-259)"
         if not self.is_assembled:
             self.assemble()
-        if not isinstance(input_mesh_vector, fem.Vector):
+        if not adapter.is_vector_like(input_mesh_vector):
             raise TypeError("input_mesh_vector must be a firedrake vector")
-        assert input_mesh_vector.size() == self.n_mesh, \
+        assert adapter.function_array(input_mesh_vector).shape[0] == self.n_mesh, \
             "input vector must be the same length as the FEM DOFs and be distributed across processes in the same way"
         ctx = self.csc.ctx
-        return self.csc.matmul(ctx.to_device(input_mesh_vector.array, np.float64)).cpu().numpy()
+        return self.csc.matmul(ctx.to_device(adapter.function_array(input_mesh_vector), np.float64)).cpu().numpy()
 
     def get_meshspace_column_vector(self, idx):
         "column idx of P as a mesh-space Vector (InterpolationMatrix.py:261-287)"

@@ -8,6 +8,7 @@ import numpy as np
 from scipy.linalg import LinAlgError
 from . import _lib
 from . import fem
+from . import adapter
 from .parallel import EnsembleComm, COMM_SELF, comm_world
 from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
@@ -19,9 +20,9 @@ class LinearSolver(object):
     def __init__(self, A, b, G, data, *, priors=[None, None, None], ensemble_comm=COMM_SELF, P=None,
                  solver_parameters=None, nullspace=None, transpose_nullspace=None, near_nullspace=None,
                  options_prefix=None):
-        if not isinstance(A, fem.Matrix):
+        if not adapter.looks_like_matrix(A):
             raise TypeError("A must be a firedrake matrix")
-        if not isinstance(b, (fem.Function, fem.Vector)):
+        if not adapter.is_function_like(b) or isinstance(b, np.ndarray):
             raise TypeError("b must be a firedrake function or vector")
         if not isinstance(G, ForcingCovariance):
             raise TypeError("G must be a forcing covariance")
@@ -36,6 +37,10 @@ class LinearSolver(object):
                 raise TypeError("priors must be a list of prior objects or None")
         if not isinstance(ensemble_comm, EnsembleComm):
             raise TypeError("ensemble_comm must be an MPI communicator created with a firedrake Ensemble")
+        # native containers, or duck-typed Firedrake-style ones (adapter.py): A over G's function space, b as a Function
+        A = adapter.as_matrix(A, G.function_space)
+        if not isinstance(b, (fem.Function, fem.Vector)):
+            b = fem.Function(G.function_space, adapter.function_array(b))
         self.solver = SparseSolver(A, P=P, solver_parameters=solver_parameters, nullspace=nullspace,
                                    transpose_nullspace=transpose_nullspace, near_nullspace=near_nullspace,
                                    options_prefix=options_prefix)
@@ -157,6 +162,32 @@ class LinearSolver(object):
         self._cache = None
         return self.mu, self.Cu
 
+    # ---- persistence of the cached prior -----------------------------------------------------
+    def save_prior(self, path):
+        "write the cached prior (x on the mesh, mu and Cu at the sensors) to ``path`` (.npz); ensemble root only"
+        if self.Cu is None or self.mu is None:
+            self.solve_prior()
+        if self.ensemble_comm.rank == 0:
+            np.savez(path, x=self._x_dev.cpu().numpy(), mu=self._mu_dev.cpu().numpy(), Cu=self._Cu_dev.cpu().numpy(),
+                     sensors=self.data.get_coords())
+
+    def load_prior(self, path):
+        "restore what ``save_prior`` wrote instead of running the n_obs solves (same mesh, same sensors)"
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        assert np.array_equal(z["sensors"], self.data.get_coords()), "the saved prior belongs to other sensor locations"
+        assert z["x"].shape[0] == self.solver.n, "the saved prior belongs to another mesh"
+        ctx = self.solver.ctx
+        self.x = fem.Function(self.G.function_space, z["x"])
+        if self.ensemble_comm.rank == 0:
+            self._x_dev, self._mu_dev = ctx.to_device(z["x"], np.float64), ctx.to_device(z["mu"], np.float64)
+            self._Cu_dev = ctx.to_device(z["Cu"], np.float64)
+            self.mu, self.Cu = z["mu"].copy(), z["Cu"].copy()
+        else:
+            self.mu, self.Cu = np.zeros(0), np.zeros((0, 0))
+        self._W_dev = self._W_cols = None
+        self._cache = None
+        return self.mu, self.Cu
+
     def _keep_factors(self):
         "keep this rank's block of W = G A^-1 P after solve_prior?  (solver parameter ``keep_factors``; default: if it fits)"
         flag = self.solver.keep_factors
@@ -273,8 +304,7 @@ class LinearSolver(object):
             coef = self._axpby(rho, t1, -rho ** 2, d2)
             m = self._aga_p(coef.reshape(-1, 1), collective=False).reshape(-1)
             out = self._axpby(scalefact, m, scalefact, self._x_dev)
-            xf = x.function if isinstance(x, fem.Vector) else x
-            xf.data[:] = out.cpu().numpy()
+            adapter.assign_function(x, out.cpu().numpy())
 
     def solve_posterior_covariance(self, scale_mean=False):
         "posterior mean and covariance at the sensors (LinearSolver.py:308-373)"
@@ -584,5 +614,4 @@ def solve_posterior_snapshots(solvers, xs, scale_mean=False):
         for i, (x, ls) in enumerate(zip(xs, solvers)):
             sf = float(np.exp(ls.params[0])) if scale_mean else 1.
             out = sf * (X[:, i] + base._x_dev)
-            xf = x.function if isinstance(x, fem.Vector) else x
-            xf.data[:] = out.cpu().numpy()
+            adapter.assign_function(x, out.cpu().numpy())

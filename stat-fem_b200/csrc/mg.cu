@@ -359,7 +359,7 @@ int mg_setup(sfem_ctx* c, int dim, const double* coords, const unsigned char* bc
     int herr = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (herr) return sfem_fail(c, SFEM_ERR_LIMIT, "mg_setup: mesh edges span more than one level-1 lattice cell; use a finer lattice");
+    if (herr) return sfem_fail(c, SFEM_ERR_LIMIT, "mg_setup: mesh edges span more than one level-1 lattice cell; use a coarser lattice");
     int center = dim == 1 ? 2 : (dim == 2 ? 12 : 62);
     lat_dinv_kernel<<<(unsigned)cdiv64(lat1.n, 256), 256, 0, c->stream>>>(lat1.n, lat1.S, center, omega, L1->stencil, L1->dinv, L1->constrained);
     KCHECK(c);

@@ -9,6 +9,7 @@ import warnings
 import numpy as np
 from . import _lib
 from . import fem
+from . import adapter
 from .parallel import EnsembleComm, COMM_SELF, ownership_range
 from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
@@ -59,9 +60,8 @@ class SparseSolver(object):
     ignored with a warning -- there is no direct-solver or CPU path."""
 
     def __init__(self, A, P=None, solver_parameters=None, nullspace=None, transpose_nullspace=None,
-                 near_nullspace=None, options_prefix=None):
-        if not isinstance(A, fem.Matrix):
-            raise TypeError("A must be a firedrake matrix")
+                 near_nullspace=None, options_prefix=None, function_space=None):
+        A = adapter.as_matrix(A, function_space)      # fem.Matrix, SciPy sparse, or a duck-typed assembled matrix
         self.A = A
         params = dict(solver_parameters or {})
         for key in params:
@@ -98,8 +98,26 @@ class SparseSolver(object):
         ctx.check(_lib.lib().sfem_set_stiffness(ctx.handle, self.n, _lib.ptr(self.dA.indptr), _lib.ptr(self.dA.indices),
                                                 _lib.ptr(self.dA.data)))
         self.bc_nodes = A.bc_nodes()
+        self._check_symmetric()
         if self.precond == 1:
             self._setup_multigrid()
+
+    def _check_symmetric(self):
+        """The covariance path uses A = A^T twice: conjugate gradients, and (G Z)^T Z standing for the reference's
+        P^T A^-1 G A^-1 P (which a direct LU would also give for a non-symmetric A).  One randomised bilinear test on the
+        device, v^T (A w) = w^T (A v), rejects a non-symmetric operator (or non-symmetric Dirichlet elimination) up
+        front instead of returning a silently different covariance."""
+        import torch
+        gen = torch.Generator(device=self.ctx.tdev)
+        gen.manual_seed(12345)
+        vw = torch.rand((self.n, 2), dtype=torch.float64, device=self.ctx.tdev, generator=gen) + 0.5
+        Avw = self.dA.matmul(vw)
+        a = float((vw[:, 0] * Avw[:, 1]).sum())
+        b = float((vw[:, 1] * Avw[:, 0]).sum())
+        scale = float((vw[:, 0] * Avw[:, 0]).sum().abs() + (vw[:, 1] * Avw[:, 1]).sum().abs()) + abs(a) + abs(b)
+        if not abs(a - b) <= 1.e-9 * scale:
+            raise ValueError("A must be symmetric (assemble it with the Dirichlet conditions eliminated symmetrically): "
+                             "v^T A w = %.12g but w^T A v = %.12g" % (a, b))
 
     def _setup_multigrid(self):
         ctx, lib = self.ctx, _lib.lib()
@@ -193,10 +211,8 @@ class SparseSolver(object):
     def solve(self, x, b):
         """firedrake-style ``solver.solve(x, b)``: homogeneous Dirichlet lifting of the right-hand side iff ``A.bcs`` is
         set -- the switch solving_utils.py:46-57 flips around the covariance solves."""
-        xf = x.function if isinstance(x, fem.Vector) else x
-        bf = b.function if isinstance(b, fem.Vector) else b
-        sol = self.solve_vector(self.ctx.to_device(bf.data, np.float64), apply_bcs=self.A.bcs is not None)
-        xf.data[:] = sol.cpu().numpy()
+        sol = self.solve_vector(self.ctx.to_device(adapter.function_array(b), np.float64), apply_bcs=self.A.bcs is not None)
+        adapter.assign_function(x, sol.cpu().numpy())
 
 
 def _aga_device(G, ls, rhs_dev):
@@ -212,11 +228,11 @@ def solve_forcing_covariance(G, ls, rhs):
         raise TypeError("G must be a ForcingCovariance object")
     if not isinstance(ls, SparseSolver):
         raise TypeError("ls must be a firedrake LinearSolver")
-    if not isinstance(rhs, fem.Vector):
+    if not adapter.is_vector_like(rhs):
         raise TypeError("rhs must be a firedrake vector")
     if not G.is_assembled:
         G.assemble()
-    out = _aga_device(G, ls, ls.ctx.to_device(rhs.array, np.float64))
+    out = _aga_device(G, ls, ls.ctx.to_device(adapter.function_array(rhs), np.float64))
     f = fem.Function(G.function_space, out.cpu().numpy())
     return f.vector()
 

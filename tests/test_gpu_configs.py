@@ -231,3 +231,142 @@ def test_block_solve_fails_loudly_on_nonfinite_input():
         B[:, 2] = 2.
         sp_.solve_block(B, X)             # and the same solver still works afterwards
         assert np.all(np.isfinite(X.cpu().numpy()))
+
+
+def _fake_firedrake_objects(c):
+    "the golden case's inputs wrapped in the Firedrake stand-ins of oracle/fake_firedrake.py (duck-typed containers)"
+    from oracle import fake_firedrake as ff
+    V = ff.FakeSpace(c["coords"], c["cells"], c["int_basis"])
+    A = sp.csr_matrix((c["A_data"], c["A_indices"], c["A_indptr"]), shape=(len(c["b"]), len(c["b"])))
+    return ff, V, ff.FakeMatrix(A, c["bc_nodes"]), ff.Function(V, np.array(c["b"], dtype=np.float64))
+
+
+@pytest.mark.parametrize("name", ["sq11_example", "sq33_cutoff", "cube9_cutoff"])
+def test_adapter_accepts_firedrake_style_objects(name):
+    """a WithGeometry-like function space, a MatrixBase-like assembled matrix and Firedrake-like
+    Function / Vector objects go through the same API (ForcingCovariance.py:74-79, LinearSolver.py:118-140) and give
+    the reference's golden results"""
+    from conftest import load_case
+    import stat_fem_b200 as stat_fem
+    c = load_case(name)
+    ff, V, A, b = _fake_firedrake_objects(c)
+    G = stat_fem.ForcingCovariance(V, float(c["sigma_f"]), float(c["l_f"]), float(c["cutoff"]), float(c["reg"]))
+    x = ff.Function(V, np.ones(V.dim())).vector()
+    y = ff.Function(V).vector()
+    G.mult(x, y)
+    assert relerr(y.gather(), c["G_ones"]) < 1e-13
+    od = stat_fem.ObsData(c["sensors"], c["data"], c["unc"])
+    ls = stat_fem.LinearSolver(A, b, G, od)
+    mu, Cu = ls.solve_prior()
+    assert relerr(mu, c["mu"]) < TOL and relerr(Cu, c["Cu"]) < TOL
+    ls.set_params(c["params"])
+    u = ff.Function(V)
+    ls.solve_posterior(u)
+    assert relerr(u.vector().gather(), c["post_mean"]) < TOL
+    u2 = ff.Function(V)
+    stat_fem.solve_posterior(A, u2, b, G, od, c["params"])
+    assert relerr(u2.vector().gather(), c["post_mean"]) < TOL
+    im = stat_fem.InterpolationMatrix(V, c["sensors"].reshape(len(c["sensors"]), -1))
+    v = ff.Function(V, np.arange(V.dim(), dtype=np.float64)).vector()
+    assert_allclose(im.interp_mesh_to_data(v), c["P"].T @ v.gather(), atol=1e-10)
+    # a bare SciPy matrix (Dirichlet nodes recognised from its identity rows) works as well
+    As = sp.csr_matrix((c["A_data"], c["A_indices"], c["A_indptr"]), shape=(V.dim(), V.dim()))
+    mu2, Cu2 = stat_fem.LinearSolver(As, b, G, od).solve_prior()
+    assert relerr(mu2, c["mu"]) < TOL and relerr(Cu2, c["Cu"]) < TOL
+    with pytest.raises(TypeError):
+        stat_fem.LinearSolver(np.eye(3), b, G, od)
+    with pytest.raises(TypeError):
+        stat_fem.ForcingCovariance(object(), 0., 0.)
+
+
+def test_user_covariance_callable_and_persistence(tmp_path):
+    """``cov=`` callables (ForcingCovariance.py:52-53, 161) and saving / restoring G and the prior"""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    from stat_fem_b200.covariance_functions import sqexp
+    import oracle
+    V, A, b = fem.poisson_problem(33, 2)
+    h = 1. / 32
+    sig, l, reg = np.log(2.e-2), np.log(1.5 * h), 1.e-8 * h ** 4 * np.exp(2 * np.log(2.e-2))
+
+    def my_sqexp(x1, x2, sigma, corr):                 # a different callable with the built-in's values
+        return sqexp(x1, x2, sigma, corr)
+
+    def matern32(x1, x2, sigma, corr):
+        from scipy.spatial.distance import cdist
+        r = cdist(np.atleast_2d(x1), np.atleast_2d(x2)) * np.exp(-corr) * np.sqrt(3.)
+        return np.exp(2. * sigma) * (1. + r) * np.exp(-r)
+
+    Gk = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg)
+    Gk.assemble()
+    Gc = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg, cov=my_sqexp)
+    Gc.assemble()
+    a, c_ = Gk.G.to_host(), Gc.G.to_host()
+    assert np.array_equal(a[0], c_[0]) and np.array_equal(a[1], c_[1])
+    assert_allclose(a[2], c_[2], rtol=1e-13, atol=0.)
+    Gm = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg, cov=matern32)
+    gd, maxnnz = Gm._compute_G_vals()
+    ref, refmax = oracle.compute_G_rows(V.coords, V.integrate_basis_functions(), sig, l, 1.e-3, reg, cov=matern32)
+    assert maxnnz == refmax
+    for i in (0, 17, 500, V.dim() - 1):
+        assert np.array_equal(gd[i][1], ref[i][1]) and gd[i][1].dtype == np.int32
+        assert_allclose(gd[i][0], ref[i][0], rtol=1e-14, atol=0.)
+    # the callable-assembled G drives the solves like any other
+    s = np.random.default_rng(3).uniform(0.05, 0.95, (12, 2))
+    od = stat_fem.ObsData(s, np.zeros(12), 2.e-3)
+    Cu_k = stat_fem.LinearSolver(A, b, Gk, od).solve_prior()[1]
+    Cu_c = stat_fem.LinearSolver(A, b, Gc, od).solve_prior()[1]
+    assert relerr(Cu_c, Cu_k) < 1e-12
+    # persistence
+    path = str(tmp_path / "G.npz")
+    Gk.save(path)
+    Gl = stat_fem.ForcingCovariance.load(V, path)
+    assert Gl.is_assembled and all(np.array_equal(p, q) for p, q in zip(Gl.G.to_host(), a))
+    ls = stat_fem.LinearSolver(A, b, Gk, od)
+    mu, Cu = ls.solve_prior()
+    ls.save_prior(str(tmp_path / "prior.npz"))
+    ls2 = stat_fem.LinearSolver(A, b, Gl, od)
+    mu2, Cu2 = ls2.load_prior(str(tmp_path / "prior.npz"))
+    assert np.array_equal(mu, mu2) and np.array_equal(Cu, Cu2)
+    th = np.array([np.log(0.7), np.log(1.e-2), np.log(0.5)])
+    assert ls2.logposterior(th) == ls.logposterior(th)
+    x1, x2 = fem.Function(V), fem.Function(V)
+    ls.set_params(th); ls2.set_params(th)
+    ls.solve_posterior(x1); ls2.solve_posterior(x2)           # ls2 has no resident W: the two-solve chain
+    assert relerr(x2.data, x1.data) < TOL
+
+
+def test_nonsymmetric_stiffness_is_rejected():
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    from stat_fem_b200.solving_utils import SparseSolver
+    V, A, b = fem.poisson_problem(17, 2)
+    bad = fem.Matrix(V, A.indptr, A.indices, A.data.copy(), A.bcs)
+    interior = np.nonzero(np.diff(A.indptr) > 1)[0][5]
+    bad.data[A.indptr[interior] + 1] *= 1.5               # one off-diagonal entry without its transpose
+    with pytest.raises(ValueError):
+        SparseSolver(bad)
+    SparseSolver(A)
+
+
+def test_forcing_covariance_long_rows_fall_back_to_all_pairs():
+    """a correlation length that keeps more than 12288 entries per row (the cap of the cell-list sort, csrc/gcov.cu) and a
+    diagonal-only 3-D case whose natural cell grid would exceed 2^28 cells: both assemble, rows match the reference formula"""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    import oracle
+    V, A, b = fem.poisson_problem(113, 2)                  # 12 769 DOF
+    sig, l = np.log(2.e-2), np.log(2.)
+    G = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, 1.e-12)
+    G.assemble()
+    assert G.max_row_nnz > 12288
+    ip, ix, v = G.G.to_host()
+    rows = [0, 56, 6000, V.dim() - 1]
+    ref, _ = oracle.compute_G_rows(V.coords, V.integrate_basis_functions(), sig, l, 1.e-3, 1.e-12, rows=rows)
+    for i in rows:
+        assert np.array_equal(ix[ip[i]:ip[i + 1]], ref[i][1])
+        assert_allclose(v[ip[i]:ip[i + 1]], ref[i][0], rtol=1e-13, atol=0.)
+    V3, A3, b3 = fem.poisson_problem(9, 3)
+    G3 = stat_fem.ForcingCovariance(V3, np.log(2.e-2), np.log(0.354), 1.e-3, 1.e-8)      # reference defaults: diagonal
+    G3.assemble()
+    assert G3.G.nnz == V3.dim()
