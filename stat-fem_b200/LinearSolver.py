@@ -225,6 +225,8 @@ class LinearSolver(object):
             return X
         if comm.rank != 0:
             return None
+        if not self.im.is_assembled:
+            self.im.assemble()
         X = ctx.empty((sp.n, ns))
         sp.solve_block(self.im.csr.matmul(Cmat.contiguous()), X)
         Wb = self.G.G.matmul(X)

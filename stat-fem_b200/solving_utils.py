@@ -111,7 +111,10 @@ class SparseSolver(object):
         gen = torch.Generator(device=self.ctx.tdev)
         gen.manual_seed(12345)
         vw = torch.rand((self.n, 2), dtype=torch.float64, device=self.ctx.tdev, generator=gen) + 0.5
-        Avw = self.dA.matmul(vw)
+        Avw = self.ctx.empty((self.n, 2))        # through THIS solver's context (the uploaded matrix may be a cached one)
+        self.ctx.check(_lib.lib().sfem_spmm_csr(self.ctx.handle, self.n, self.dA.nnz, _lib.ptr(self.dA.indptr),
+                                                _lib.ptr(self.dA.indices), _lib.ptr(self.dA.data), 2, _lib.ptr(vw), 2,
+                                                _lib.ptr(Avw), 2))
         a = float((vw[:, 0] * Avw[:, 1]).sum())
         b = float((vw[:, 1] * Avw[:, 0]).sum())
         scale = float((vw[:, 0] * Avw[:, 0]).sum().abs() + (vw[:, 1] * Avw[:, 1]).sum().abs()) + abs(a) + abs(b)

@@ -342,8 +342,9 @@ def test_nonsymmetric_stiffness_is_rejected():
     from stat_fem_b200.solving_utils import SparseSolver
     V, A, b = fem.poisson_problem(17, 2)
     bad = fem.Matrix(V, A.indptr, A.indices, A.data.copy(), A.bcs)
-    interior = np.nonzero(np.diff(A.indptr) > 1)[0][5]
-    bad.data[A.indptr[interior] + 1] *= 1.5               # one off-diagonal entry without its transpose
+    rows = np.repeat(np.arange(V.dim()), np.diff(A.indptr))
+    k = np.nonzero((A.indices != rows) & (A.data != 0.))[0][7]
+    bad.data[k] *= 1.5                                     # one off-diagonal entry no longer equal to its transpose
     with pytest.raises(ValueError):
         SparseSolver(bad)
     SparseSolver(A)
@@ -367,6 +368,8 @@ def test_forcing_covariance_long_rows_fall_back_to_all_pairs():
         assert np.array_equal(ix[ip[i]:ip[i + 1]], ref[i][1])
         assert_allclose(v[ip[i]:ip[i + 1]], ref[i][0], rtol=1e-13, atol=0.)
     V3, A3, b3 = fem.poisson_problem(9, 3)
-    G3 = stat_fem.ForcingCovariance(V3, np.log(2.e-2), np.log(0.354), 1.e-3, 1.e-8)      # reference defaults: diagonal
+    # nugget so large that nothing but the diagonal passes the ratio test: the search radius is empty and the natural
+    # "any small cell" grid (2048 per direction) would have 2^33 cells
+    G3 = stat_fem.ForcingCovariance(V3, np.log(2.e-2), np.log(0.354), 1.e-3, 1.e-3)
     G3.assemble()
     assert G3.G.nnz == V3.dim()
