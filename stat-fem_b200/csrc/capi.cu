@@ -14,6 +14,7 @@ int cg_solve_block(sfem_ctx* c, int k, const double* B, int64_t ldb, double* X, 
 int scatter_columns(sfem_ctx* c, int64_t n, const int64_t* colptr, const int32_t* rows, const double* vals,
                     int64_t col_begin, int k, double* B, int64_t ldb);
 void gcov_free(sfem_ctx* c);
+void dense_graphs_free(sfem_ctx* c);
 void prof_free(sfem_ctx* c);
 void prof_collect(sfem_ctx* c);
 void prof_reset(sfem_ctx* c);
@@ -109,6 +110,7 @@ int sfem_destroy(sfem_ctx* c) {
     mg_free(c);
     gcov_free(c);
     prof_free(c);
+    dense_graphs_free(c);
     if (c->A_dinv) sfem_dev_free(c->A_dinv);
     if (c->scratch) sfem_dev_free(c->scratch);
     if (c->dense_tmp) sfem_dev_free(c->dense_tmp);

@@ -74,6 +74,10 @@ struct sfem_ctx {
     void* dense_tmp = nullptr; size_t dense_tmp_bytes = 0;   // panel / trtri temporaries of chol.cu (owned, grows)
     cudaStream_t aux_stream = nullptr;                        // look-ahead stream of the blocked Cholesky (owned, lazy)
     cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_head = nullptr;
+
+    // ---- CUDA graphs of the fused value+gradient evaluation (dense_ops.cu), keyed by the problem's device pointers ----
+    struct DenseGraph { const void* key[8] = {nullptr}; void* exec = nullptr; long long launches = 0; int failed = 0; };
+    std::vector<DenseGraph> dense_graphs;
 };
 
 int sfem_fail(sfem_ctx* c, int code, const char* fmt, ...);

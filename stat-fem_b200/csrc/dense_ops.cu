@@ -1,6 +1,7 @@
 // K13 / K14: model-discrepancy kernel matrices and the fused dense reductions behind logposterior / logpost_deriv /
 // solve_posterior_covariance (ObsData.py:131-214, LinearSolver.py:351-367, 600-613, 659-681).
 #include "common.cuh"
+#include <cstdlib>
 
 int potrf_lower(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev);
 int potrs_lower(sfem_ctx* c, int n, const double* L, int64_t ldl, const double* dinv, int k, double* B, int64_t ldb);
@@ -30,10 +31,11 @@ __device__ __forceinline__ double r2_pair(const double* __restrict__ X, const do
 __global__ void kernel_matrix_kernel(int m, int n, int d, const double* __restrict__ X1, const double* __restrict__ X2,
                                      double e2s, double em2l, const double* __restrict__ unc, int unc_is_vector,
                                      double rho2, const double* __restrict__ Cu, int64_t ldcu, int which,
-                                     double* __restrict__ M, int64_t ldm) {
+                                     double* __restrict__ M, int64_t ldm, const double* __restrict__ dp) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= m || j >= n) return;
+    if (dp) { e2s = dp[0]; em2l = dp[1]; rho2 = dp[2]; }      // scalars from device memory: the launch can sit in a CUDA graph
     double r2 = r2_pair(X1, X2, d, i, j);
     double kv = __dmul_rn(e2s, exp(__dmul_rn(__dmul_rn(-0.5, r2), em2l)));
     double v;
@@ -59,8 +61,9 @@ __global__ void kernel_matrix_kernel(int m, int n, int d, const double* __restri
 
 // z = a*x + b*y  (vectors)
 __global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
-                             double* __restrict__ z) {
+                             double* __restrict__ z, const double* __restrict__ db) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (db) b = *db;
     if (i < n) z[i] = a * x[i] + (y ? b * y[i] : 0.0);
 }
 
@@ -102,8 +105,9 @@ __global__ void dots_kernel(int n, DotJob j0, DotJob j1, DotJob j2, double* __re
 __global__ void __launch_bounds__(256) grad_reduce_kernel(int n, int d, const double* __restrict__ X, double e2s,
                                                           double em2l, const double* __restrict__ alpha,
                                                           const double* __restrict__ Kinv, const double* __restrict__ Cu,
-                                                          double* __restrict__ partials) {
+                                                          double* __restrict__ partials, const double* __restrict__ dp) {
     __shared__ double sh[6][256];
+    if (dp) { e2s = dp[0]; em2l = dp[1]; }
     double s[6] = {0, 0, 0, 0, 0, 0};
     int64_t tot = (int64_t)n * n;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
@@ -139,11 +143,11 @@ __global__ void grad_final_kernel(int nblk, const double* __restrict__ partials,
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int build_matrix(sfem_ctx* c, int n, int d, const double* Xs, double sigma, double l, const double* unc, int unc_vec,
-                 double rho2, const double* Cu, int which, double* M) {
+                 double rho2, const double* Cu, int which, double* M, const double* dp = nullptr) {
     ProfScope ps(c, TAG_DENSE_MISC, 8.0 * (double)n * n * (Cu ? 2.0 : 1.0), 0.0);
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
     kernel_matrix_kernel<<<grd, blk, 0, c->stream>>>(n, n, d, Xs, Xs, exp(2.0 * sigma), exp(-2.0 * l), unc, unc_vec, rho2,
-                                                     Cu, n, which, M, n);
+                                                     Cu, n, which, M, n, dp);
     KCHECK(c);
     return SFEM_OK;
 }
@@ -161,14 +165,14 @@ int dense_cov_matrix(sfem_ctx* c, int m, int n, int d, const double* X1, const d
     if (m <= 0 || n <= 0) return SFEM_OK;
     dim3 blk(32, 8), grd((n + 31) / 32, (m + 7) / 8);
     kernel_matrix_kernel<<<grd, blk, 0, c->stream>>>(m, n, d, X1, X2, exp(2.0 * sigma), exp(-2.0 * l), nullptr, 0, 0.0,
-                                                     nullptr, 0, which, M, n);
+                                                     nullptr, 0, which, M, n, nullptr);
     KCHECK(c);
     return SFEM_OK;
 }
 
 int dense_axpby(sfem_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z) {
     if (n <= 0) return SFEM_OK;
-    axpby_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>((int)n, a, x, b, y, z);
+    axpby_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c->stream>>>((int)n, a, x, b, y, z, nullptr);
     KCHECK(c);
     return SFEM_OK;
 }
@@ -304,22 +308,26 @@ static DenseWs carve(int n, void* work) {
 
 // value = 0.5 (n log 2pi + log|KCu| + r^T KCu^-1 r),  r = y - rho mu;  optional gradient (3 doubles).
 // theta = (log rho, log sigma_eta, log l_eta).  Returns SFEM_ERR_NOT_SPD if the factorisation breaks down.
-int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
-                  const double* mu, const double* Cu, const double* theta_host, double* value_host, double* grad_host,
-                  void* work, size_t work_bytes) {
-    if (work_bytes < dense_workspace_bytes(n)) return sfem_fail(c, SFEM_ERR_ARG, "logpost: workspace too small");
-    DenseWs w = carve(n, work);
-    double rho = exp(theta_host[0]);
-    double sigma = theta_host[1], l = theta_host[2];
+//
+// Everything that depends on theta reaches the kernels through four doubles in device memory (dp = e^{2 sigma},
+// e^{-2 l}, rho^2, -rho), uploaded from the context's pinned buffer, and the results come back into the same pinned
+// buffer: the whole evaluation is a fixed sequence of ~170 launches, copies and cross-stream events that does not
+// depend on theta.  For the fused value+gradient evaluation (the MAP loop, estimation.py:92-93) that sequence is
+// captured once per (context, problem) into a CUDA graph and replayed: an L-BFGS-B fit re-evaluates it 50-100 times,
+// eight fits share one GPU from eight host threads, and issuing the launches one by one was what bounded them.
+static int logpost_enqueue(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
+                           const double* mu, const double* Cu, bool want_grad, DenseWs& w, double* hbuf) {
     double* r = w.vec;
     double* alpha = w.vec + n;
-    int rc = build_matrix(c, n, d, Xs, sigma, l, unc, unc_vec, rho * rho, Cu, 0, w.M);
+    double* dp = w.small + 48;
+    CUDA_TRY(c, cudaMemcpyAsync(dp, hbuf, sizeof(double) * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = build_matrix(c, n, d, Xs, 0.0, 0.0, unc, unc_vec, 0.0, Cu, 0, w.M, dp);
     if (rc) return rc;
-    axpby_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 1.0, y, -rho, mu, r);
+    axpby_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 1.0, y, 0.0, mu, r, dp + 3);
     KCHECK(c);
     rc = potrf_lower(c, n, w.M, n, w.dinv, w.info);
     if (rc) return rc;
-    if (grad_host) {
+    if (want_grad) {
         // the gradient needs inv(KCu) anyway (traces): use it for alpha = inv(KCu) r as well
         rc = potri_lower(c, n, w.M, n, w.dinv, w.W, w.Kinv);
         if (rc) return rc;
@@ -336,19 +344,95 @@ int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, 
     DotJob j0{r, alpha}, j1{mu, alpha}, jn{nullptr, nullptr};
     dots_kernel<<<1, 256, 0, c->stream>>>(n, j0, j1, jn, w.small);
     KCHECK(c);
-    if (grad_host) {
+    if (want_grad) {
         int nblk = 4 * SFEM_NUM_SMS;
         ProfScope ps(c, TAG_DENSE_MISC, 16.0 * (double)n * n, 0.0);
-        grad_reduce_kernel<<<nblk, 256, 0, c->stream>>>(n, d, Xs, exp(2.0 * sigma), exp(-2.0 * l), alpha, w.Kinv, Cu, w.partials);
+        grad_reduce_kernel<<<nblk, 256, 0, c->stream>>>(n, d, Xs, 0.0, 0.0, alpha, w.Kinv, Cu, w.partials, dp);
         KCHECK(c);
         grad_final_kernel<<<1, 32, 0, c->stream>>>(nblk, w.partials, w.small + 16);
         KCHECK(c);
     }
-    double h[32];
-    int info = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(h, w.small, sizeof(double) * 32, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(hbuf + 8, w.small, sizeof(double) * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(hbuf + 40, w.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return SFEM_OK;
+}
+
+void dense_graphs_free(sfem_ctx* c) {
+    for (auto& g : c->dense_graphs)
+        if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+    c->dense_graphs.clear();
+}
+
+int dense_logpost(sfem_ctx* c, int n, int d, const double* Xs, const double* y, const double* unc, int unc_vec,
+                  const double* mu, const double* Cu, const double* theta_host, double* value_host, double* grad_host,
+                  void* work, size_t work_bytes) {
+    if (work_bytes < dense_workspace_bytes(n)) return sfem_fail(c, SFEM_ERR_ARG, "logpost: workspace too small");
+    DenseWs w = carve(n, work);
+    const double rho = exp(theta_host[0]);
+    const double sigma = theta_host[1], l = theta_host[2];
+    double* hbuf = reinterpret_cast<double*>(static_cast<unsigned char*>(c->pinned) + 1024);     // 4 in | 32 out | info
+    hbuf[0] = exp(2.0 * sigma); hbuf[1] = exp(-2.0 * l); hbuf[2] = rho * rho; hbuf[3] = -rho;
+    const bool want_grad = grad_host != nullptr;
+    static int use_graphs = -1;
+    if (use_graphs < 0) {
+        const char* e = getenv("SFEM_DENSE_GRAPH");
+        use_graphs = (e && e[0] == '0') ? 0 : 1;
+    }
+    int rc = SFEM_OK;
+    bool done = false;
+    if (use_graphs && want_grad && c->prof_mask == 0 && n > 256) {
+        const void* key[8] = {Xs, y, unc, mu, Cu, work, (const void*)(intptr_t)n, (const void*)(intptr_t)(d * 2 + unc_vec)};
+        sfem_ctx::DenseGraph* hit = nullptr;
+        for (auto& g : c->dense_graphs)
+            if (memcmp(g.key, key, sizeof(key)) == 0) { hit = &g; break; }
+        if (hit && hit->exec) {
+            CUDA_TRY(c, cudaGraphLaunch((cudaGraphExec_t)hit->exec, c->stream));
+            c->launches += hit->launches;
+            done = true;
+        } else if (hit && !hit->failed) {
+            // second evaluation of this problem: every temporary has its final size now -- record it.  (The legacy
+            // default stream cannot be captured: such a context stays on the direct path.)
+            long long l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = logpost_enqueue(c, n, d, Xs, y, unc, unc_vec, mu, Cu, true, w, hbuf);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                if (rc == SFEM_OK && ce == cudaSuccess && graph) {
+                    cudaGraphExec_t exec = nullptr;
+                    if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                        hit->exec = exec;
+                        hit->launches = c->launches - l0;
+                    }
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();
+            c->launches = l0;
+            rc = SFEM_OK;
+            if (hit->exec) {
+                CUDA_TRY(c, cudaGraphLaunch((cudaGraphExec_t)hit->exec, c->stream));
+                c->launches += hit->launches;
+                done = true;
+            } else {
+                hit->failed = 1;      // capture not possible here: stay on the direct path for this problem
+            }
+        } else if (!hit) {
+            if (c->dense_graphs.size() >= 4) {        // small cache: a context serves one data set at a time
+                if (c->dense_graphs.front().exec) cudaGraphExecDestroy((cudaGraphExec_t)c->dense_graphs.front().exec);
+                c->dense_graphs.erase(c->dense_graphs.begin());
+            }
+            sfem_ctx::DenseGraph g;
+            memcpy(g.key, key, sizeof(key));
+            c->dense_graphs.push_back(g);
+        }
+    }
+    if (!done) {
+        rc = logpost_enqueue(c, n, d, Xs, y, unc, unc_vec, mu, Cu, want_grad, w, hbuf);
+        if (rc) return rc;
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const double* h = hbuf + 8;
+    int info = *reinterpret_cast<const int*>(hbuf + 40);
     if (info != 0) return sfem_fail(c, SFEM_ERR_NOT_SPD, "logpost: covariance matrix not positive definite (pivot %d)", info);
     const double LOG2PI = 1.8378770664093454835606594728112;
     if (value_host) *value_host = 0.5 * ((double)n * LOG2PI + h[8] + h[0]);

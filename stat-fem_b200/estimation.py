@@ -73,7 +73,9 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, polish=False, accept_p
     if world.size > 1:
         ls.share_prior()
     mine = [i for i in range(ndata) if i % world.size == world.rank]
-    conc = bool(concurrent) and len(mine) > 1
+    # every fit gets its own stream context, even a single one: a private (non-default) stream is what lets the library
+    # replay the evaluation as a CUDA graph (csrc/dense_ops.cu)
+    conc = bool(concurrent) and len(mine) > 0
     solvers = []
     for i, od in enumerate(datas):
         own_stream = conc and i in mine

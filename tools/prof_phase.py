@@ -64,7 +64,10 @@ def phase_solve(argv):
 def phase_dense(argv):
     nobs = int(argv[0]) if len(argv) > 0 else 4096
     reps = int(argv[1]) if len(argv) > 1 else 3
-    ctx = _lib.new_context()
+    graph = len(argv) > 2 and argv[2] == "graph"      # private stream, no per-family timers: the CUDA-graph replay path
+    ctx = _lib.new_stream_context() if graph else _lib.new_context()
+    if graph:
+        torch.cuda.set_stream(ctx.tstream)
     lib = _lib.lib()
     rng = np.random.default_rng(0)
     Xs = rng.uniform(0.02, 0.98, (nobs, 2))
@@ -86,7 +89,9 @@ def phase_dense(argv):
         ctx.check(lib.sfem_logpost(ctx.handle, nobs, 2, _lib.ptr(dXs), _lib.ptr(y), _lib.ptr(unc), 0, _lib.ptr(mu), _lib.ptr(Cu),
                                    theta, C.byref(val), grad if with_grad else None, C.c_void_p(base + off), int(work.numel() - off)))
     ev(True)
-    ctx.profile_enable(0xffffffff)
+    ev(True)
+    if not graph:
+        ctx.profile_enable(0xffffffff)
     ms_v, _ = dev_time(lambda: ev(False), reps)
     ms_g, _ = dev_time(lambda: ev(True), reps)
     print("n_obs=%d  logposterior %.3f ms (%.2f TFLOP/s on n^3/3)   value+gradient %.3f ms (%.2f TFLOP/s on n^3)  value %.12g" %
