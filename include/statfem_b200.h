@@ -192,6 +192,35 @@ int sfem_dense_solve(sfem_ctx* ctx, int n_obs, int dim, const double* Xs, const 
                      double sigma, double l, double rho2, const double* Cu, const double* b, double* x, void* work,
                      size_t work_bytes);
 
+/* ---- The sharded covariance assembly (ensemble parallelism of solving_utils.py:117-159) over NCCL ---------------------
+ * The reference splits the sensor columns over `ensemble_comm` (contiguous ownership, lines 117-123), every rank runs its
+ * own solves (139-142) and the rows are gathered on ensemble rank 0 (146-159).  Here: one context per GPU, one NCCL
+ * communicator per context, and ONE call per rank.  NCCL is bound at run time (dlopen of libnccl.so.2); a single rank
+ * needs neither NCCL nor a communicator.
+ *
+ * sfem_nccl_unique_id : rank 0 fills 128 bytes (an ncclUniqueId); the caller hands them to every rank (MPI_Bcast, a file).
+ * sfem_comm_init      : collective over the nranks contexts; sfem_comm_attach adopts an ncclComm_t the caller owns.
+ * sfem_comm_bcast     : in-place broadcast of a device buffer (e.g. the cached prior x, mu, Cu for per-rank MAP fits).
+ * sfem_prior_cov      : this rank owns sensor columns [col_begin, col_end) -- the ranks' ranges must tile [0, n_obs) in
+ *                       rank order (PETSc's rule does).  Computes Z_r = A^-1 P[:, J_r] by block PCG in blocks of
+ *                       `block_cols` columns (0: 384), W_r = G Z_r, and rows J_r of Cu = (G Z)^T Z, receiving the other
+ *                       ranks' Z blocks round a ring (ncclSend / ncclRecv on a second stream, row chunks, double-buffered,
+ *                       overlapped with the DMMA GEMM); the rows are gathered into Cu_out (n_obs x n_obs, row-major) on
+ *                       rank 0.  P is CSC (device), G CSR (device, the output of sfem_gcov_fill), A the matrix of
+ *                       sfem_set_stiffness (+ sfem_mg_setup when precond = 1).  Z_out / W_out: optional n x (col_end -
+ *                       col_begin) device blocks that receive Z_r and W_r (NULL: temporaries).  Cu_out may be NULL on
+ *                       ranks other than 0.  iters_max_out_host: largest CG iteration count of any block.
+ *                       Collective: every rank of the communicator must call it. */
+int sfem_nccl_unique_id(void* id_out_128_bytes_host);
+int sfem_comm_init(sfem_ctx* ctx, const void* unique_id_128_bytes_host, int rank, int nranks);
+int sfem_comm_attach(sfem_ctx* ctx, void* nccl_comm, int rank, int nranks);
+int sfem_comm_destroy(sfem_ctx* ctx);
+int sfem_comm_bcast(sfem_ctx* ctx, void* device_buffer, size_t bytes, int root);
+int sfem_prior_cov(sfem_ctx* ctx, int64_t n_obs, const int64_t* P_colptr, const int32_t* P_rows, const double* P_vals,
+                   const int64_t* G_indptr, const int32_t* G_indices, const double* G_vals, int64_t col_begin,
+                   int64_t col_end, int block_cols, int precond, double rtol, double atol, int max_it, double* Z_out,
+                   double* W_out, double* Cu_out, int* iters_max_out_host);
+
 #ifdef __cplusplus
 }
 #endif

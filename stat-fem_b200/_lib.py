@@ -26,6 +26,7 @@ EXPORTS = [
     "sfem_profile_tag_name", "sfem_profile_read", "sfem_csr_unsym_count", "sfem_csr_unsym_fill", "sfem_rows_axpy",
     "sfem_rows_gather", "sfem_dgemm_lower", "sfem_mirror_lower", "sfem_tile_apply_one",
     "sfem_b84_build", "sfem_b84_spmm", "sfem_b84_free", "sfem_skinny_gemm", "sfem_sym_fold",
+    "sfem_nccl_unique_id", "sfem_comm_init", "sfem_comm_attach", "sfem_comm_destroy", "sfem_comm_bcast", "sfem_prior_cov",
 ]
 
 
@@ -83,6 +84,12 @@ def load_library():
         "sfem_b84_free": (i32, [vp, vp]),
         "sfem_tile_apply_one": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64),
                                       C.POINTER(i32)]),
+        "sfem_nccl_unique_id": (i32, [vp]),
+        "sfem_comm_init": (i32, [vp, vp, i32, i32]),
+        "sfem_comm_attach": (i32, [vp, vp, i32, i32]),
+        "sfem_comm_destroy": (i32, [vp]),
+        "sfem_comm_bcast": (i32, [vp, vp, sz, i32]),
+        "sfem_prior_cov": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, f64, f64, i32, vp, vp, vp, C.POINTER(i32)]),
         "sfem_sym_fold": (i32, [vp, i32, i32, vp, i64]),
         "sfem_skinny_gemm": (i32, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64]),
         "sfem_dense_solve": (i32, [vp, i32, i32, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, sz]),

@@ -60,6 +60,16 @@ int dense_posterior_cov(sfem_ctx* c, int n, int d, const double* Xs, const doubl
 int dense_solve_shifted(sfem_ctx* c, int n, int d, const double* Xs, const double* unc, int unc_vec, double sigma, double l,
                         double rho2, const double* Cu, const double* b, double* x, void* work, size_t work_bytes);
 
+int sharded_unique_id(void* id_out);
+int sharded_comm_init(sfem_ctx* c, const void* id128, int rank, int nranks);
+int sharded_comm_attach(sfem_ctx* c, void* nccl_comm_handle, int rank, int nranks);
+int sharded_comm_destroy(sfem_ctx* c);
+int sharded_bcast(sfem_ctx* c, void* buf, size_t bytes, int root);
+int sharded_prior_cov(sfem_ctx* c, int64_t n_obs, const int64_t* P_colptr, const int32_t* P_rows, const double* P_vals,
+                      const int64_t* G_indptr, const int32_t* G_indices, const double* G_vals, int64_t col_begin,
+                      int64_t col_end, int block_cols, int precond, double rtol, double atol, int max_it, double* Z_out,
+                      double* W_out, double* Cu_out, int* iters_max_out_host);
+
 thread_local cudaStream_t sfem_tls_stream = nullptr;
 
 #define GUARD(ctx)                   \
@@ -107,6 +117,7 @@ int sfem_destroy(sfem_ctx* c) {
     cudaSetDevice(c->device);
     sfem_tls_stream = c->stream;
     cudaStreamSynchronize(c->stream);
+    sharded_comm_destroy(c);
     mg_free(c);
     gcov_free(c);
     prof_free(c);
@@ -311,6 +322,32 @@ int sfem_b84_free(sfem_ctx* c, void* matrix) {
 int sfem_mirror_lower(sfem_ctx* c, int n, double* A, int64_t lda) {
     GUARD(c);
     return mirror_lower(c, n, A, lda);
+}
+
+int sfem_nccl_unique_id(void* id_out_128_bytes_host) { return sharded_unique_id(id_out_128_bytes_host); }
+int sfem_comm_init(sfem_ctx* c, const void* unique_id_128_bytes_host, int rank, int nranks) {
+    GUARD(c);
+    return sharded_comm_init(c, unique_id_128_bytes_host, rank, nranks);
+}
+int sfem_comm_attach(sfem_ctx* c, void* nccl_comm, int rank, int nranks) {
+    GUARD(c);
+    return sharded_comm_attach(c, nccl_comm, rank, nranks);
+}
+int sfem_comm_destroy(sfem_ctx* c) {
+    GUARD(c);
+    return sharded_comm_destroy(c);
+}
+int sfem_comm_bcast(sfem_ctx* c, void* device_buffer, size_t bytes, int root) {
+    GUARD(c);
+    return sharded_bcast(c, device_buffer, bytes, root);
+}
+int sfem_prior_cov(sfem_ctx* c, int64_t n_obs, const int64_t* P_colptr, const int32_t* P_rows, const double* P_vals,
+                   const int64_t* G_indptr, const int32_t* G_indices, const double* G_vals, int64_t col_begin,
+                   int64_t col_end, int block_cols, int precond, double rtol, double atol, int max_it, double* Z_out,
+                   double* W_out, double* Cu_out, int* iters_max_out_host) {
+    GUARD(c);
+    return sharded_prior_cov(c, n_obs, P_colptr, P_rows, P_vals, G_indptr, G_indices, G_vals, col_begin, col_end, block_cols,
+                             precond, rtol, atol, max_it, Z_out, W_out, Cu_out, iters_max_out_host);
 }
 
 int sfem_sym_fold(sfem_ctx* c, int n, int nblocks, double* A, int64_t lda) {

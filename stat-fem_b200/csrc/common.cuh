@@ -75,6 +75,11 @@ struct sfem_ctx {
     cudaStream_t aux_stream = nullptr;                        // look-ahead stream of the blocked Cholesky (owned, lazy)
     cudaEvent_t ev_main = nullptr, ev_aux = nullptr, ev_head = nullptr;
 
+    // ---- ensemble communicator of the sharded covariance assembly (sharded.cu; NCCL bound at run time) ---------------
+    void* comm = nullptr; int comm_owned = 0, comm_rank = 0, comm_size = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_recv[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+
     // ---- CUDA graphs of the fused value+gradient evaluation (dense_ops.cu), keyed by the problem's device pointers ----
     struct DenseGraph { const void* key[8] = {nullptr}; void* exec = nullptr; long long launches = 0; int failed = 0; };
     std::vector<DenseGraph> dense_graphs;

@@ -322,3 +322,42 @@ def test_covariance_functions_and_obsdata(env):
     assert cf.sqexp(np.array([1., 2.]), np.array([[1., 2.], [2., 4.]]), 0., 0.).shape == (1, 2)
     h = cf.sqexp_hessian(z["x1_2"], z["x2_2"], np.log(0.7), np.log(0.3))
     assert h.shape == (2, 2, 9, 13) and np.allclose(h[0, 0], 4. * z["sqexp_2"])
+
+
+def test_prior_cov_entry_point_single_rank():
+    """sfem_prior_cov (the sharded covariance assembly of the C ABI, include/statfem_b200.h) with one rank -- no
+    communicator needed -- against LinearSolver.solve_prior; the multi-rank exchange is exercised by
+    tools/cabi_sharded_check.py on a multi-GPU box (profiles/r02_cabi_sharded.log)."""
+    import ctypes as C
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem, _lib
+    from stat_fem_b200.solving_utils import SparseSolver
+    lib = _lib.lib()
+    V, A, b = fem.poisson_problem(65, 2)
+    h = 1. / 64
+    sig, l = np.log(2.e-2), np.log(1.5 * h)
+    reg = 1.e-8 * h ** 4 * np.exp(2 * sig)
+    for nobs in (40, 300):           # CSR kernel / 8x4-block form of W = G Z
+        sensors = np.random.default_rng(1).uniform(0.02, 0.98, (nobs, 2))
+        G = stat_fem.ForcingCovariance(V, sig, l, 1.e-3, reg)
+        G.assemble()
+        sp_ = SparseSolver(A)
+        ctx = sp_.ctx
+        im = stat_fem.InterpolationMatrix(V, sensors)
+        im.assemble()
+        ctx.check(lib.sfem_comm_init(ctx.handle, None, 0, 1))
+        Cu = ctx.empty((nobs, nobs))
+        Z = ctx.empty((V.dim(), nobs))
+        iters = C.c_int(0)
+        ctx.check(lib.sfem_prior_cov(ctx.handle, nobs, _lib.ptr(im.csc.indptr), _lib.ptr(im.csc.indices), _lib.ptr(im.csc.data),
+                                     _lib.ptr(G.G.indptr), _lib.ptr(G.G.indices), _lib.ptr(G.G.data), 0, nobs, 128, 1, 1.e-12, 0.,
+                                     500, _lib.ptr(Z), None, _lib.ptr(Cu), C.byref(iters)))
+        od = stat_fem.ObsData(sensors, np.zeros(nobs), 2.e-3)
+        ls = stat_fem.LinearSolver(A, b, G, od)
+        ref = ls.solve_prior()[1]
+        assert relerr(Cu.cpu().numpy(), ref) < 1e-10 and 0 < iters.value < 30
+        # bad column range: reported, not silently accepted
+        rc = lib.sfem_prior_cov(ctx.handle, nobs, _lib.ptr(im.csc.indptr), _lib.ptr(im.csc.indices), _lib.ptr(im.csc.data),
+                                _lib.ptr(G.G.indptr), _lib.ptr(G.G.indices), _lib.ptr(G.G.data), 1, nobs, 128, 1, 1.e-12, 0., 500,
+                                None, None, _lib.ptr(Cu), None)
+        assert rc == _lib.SFEM_ERR_ARG
