@@ -373,3 +373,40 @@ def test_forcing_covariance_long_rows_fall_back_to_all_pairs():
     G3 = stat_fem.ForcingCovariance(V3, np.log(2.e-2), np.log(0.354), 1.e-3, 1.e-3)
     G3.assemble()
     assert G3.G.nnz == V3.dim()
+
+
+@pytest.mark.parametrize("nodes,jitter", [(129, 0.25), (200, 0.0), (97, 0.3)])
+def test_block_solve_on_jittered_and_non_aligned_meshes(nodes, jitter):
+    """The lattice multigrid only sees DOF coordinates and the CSR matrix: an irregular mesh (interior nodes moved by up to
+    `jitter` mesh widths, same connectivity, stiffness re-assembled) and a lattice-unaligned size (200^2 nodes: the
+    stiffness operator does not get the tensor-core tile form there and runs the scalar tile kernel -- the documented gate
+    of csrc/tileop.cu) must still converge in a handful of iterations to the direct solution."""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    from stat_fem_b200.solving_utils import SparseSolver
+    from oracle.solver import _DirectSolver
+    base = fem.UnitSquareMesh(nodes - 1, nodes - 1)
+    coords = base.coords.copy()
+    rng = np.random.default_rng(8)
+    h = 1. / (nodes - 1)
+    interior = np.setdiff1d(np.arange(coords.shape[0]), base.boundary_nodes())
+    coords[interior] += jitter * h * rng.uniform(-1., 1., (len(interior), 2))
+    mesh = fem.Mesh(coords, base.cells)
+    V = fem.FunctionSpace(mesh, "CG", 1)
+    bc = fem.DirichletBC(V, 0., base.boundary_nodes())
+    A = fem.assemble_stiffness(V, bcs=bc)
+    sensors = rng.uniform(0.05, 0.95, (48, 2))
+    im = stat_fem.InterpolationMatrix(V, sensors)
+    im.assemble()
+    sp_ = SparseSolver(A)
+    Z = sp_.ctx.empty((V.dim(), 48))
+    sp_.solve_columns(im.csc, 0, 48, Z)
+    assert max(sp_.block_iterations) <= 16, sp_.block_iterations
+    assert sp_.last_relres.max() < 1e-11
+    lu = _DirectSolver(A.to_scipy(), A.bc_nodes())
+    Zh = Z.cpu().numpy()
+    P = im.interp.toarray()
+    for j in (0, 17, 47):
+        ref = lu.solve(P[:, j], bcs_on=False)
+        assert relerr(Zh[:, j], ref) < 1e-9
+    print("nodes", nodes, "jitter", jitter, "iterations", sp_.block_iterations, "levels", sp_.mg_levels)
