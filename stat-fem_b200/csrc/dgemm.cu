@@ -347,6 +347,17 @@ int dgemm_batched(sfem_ctx* c, int opA, int opB, int M, int N, int64_t K, double
         if (splits > maxs) splits = (int)maxs;
         if (splits < 1) splits = 1;
     }
+    // lower-only products with a very long K (Cu = (S Z)^T Z: 528 tiles of 3.4e10 flop each at 4096 sensors): the last
+    // wave of tiles leaves most SMs idle (528 / 148 = 3.57 -> 4 waves); cutting K into a few chunks shortens the tail
+    if (splits == 1 && p.lower_only && !p.tri_k && batch == 1 && !(flags & 24) && tb == 128 && K >= 65536) {
+        int64_t tmn = p.tiles_m < p.tiles_n ? p.tiles_m : p.tiles_n;
+        int64_t eff = (int64_t)p.tiles_m * tmn - tmn * (tmn - 1) / 2;
+        double best = (double)((eff + SFEM_NUM_SMS - 1) / SFEM_NUM_SMS);
+        for (int sct = 2; sct <= 8; ++sct) {
+            double waves = (double)((eff * sct + SFEM_NUM_SMS - 1) / SFEM_NUM_SMS) / sct;
+            if (waves < 0.97 * best) { best = waves; splits = sct; }
+        }
+    }
     int64_t kchunk = K;
     if (splits > 1) {
         kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
