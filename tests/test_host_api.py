@@ -182,3 +182,85 @@ def test_lattice_choice():
         lo, hi, m1 = _lattice_nodes(np.stack(np.meshgrid(xs, xs), -1).reshape(-1, 2)) if nodes < 200 else \
             _lattice_nodes(np.stack([np.tile(xs, nodes), np.repeat(xs, nodes)], 1))
         assert m1 == [expect, expect], (nodes, m1)
+
+
+def test_adapter_reduces_firedrake_style_objects_to_arrays():
+    """adapter.py on the Firedrake stand-ins of oracle/fake_firedrake.py (no GPU involved): coordinates, cells, lumped
+    integrals, CSR, Dirichlet nodes, coefficient arrays; anything else is a TypeError with the reference's message"""
+    import scipy.sparse as sp
+    from conftest import load_case
+    from stat_fem_b200 import adapter, fem
+    from oracle import fake_firedrake as ff
+    c = load_case("sq11_example")
+    V = ff.FakeSpace(c["coords"], c["cells"], c["int_basis"])
+    S = adapter.as_function_space(V)
+    assert isinstance(S, fem.P1Space) and S.origin is V and adapter.as_function_space(V) is S      # cached on the object
+    assert np.array_equal(S.coords, c["coords"]) and np.array_equal(S.cell_node_list, c["cells"])
+    assert np.array_equal(S.integrate_basis_functions(), c["int_basis"])
+    V2 = ff.FakeSpace(c["coords"], c["cells"], None)          # no lumped integrals supplied: computed from the P1 cells
+    np.testing.assert_allclose(adapter.as_function_space(V2).integrate_basis_functions(), c["int_basis"], rtol=1e-12)
+    n = len(c["b"])
+    A = sp.csr_matrix((c["A_data"], c["A_indices"], c["A_indptr"]), shape=(n, n))
+    M = adapter.as_matrix(ff.FakeMatrix(A, c["bc_nodes"]), V)
+    assert isinstance(M, fem.Matrix) and np.array_equal(M.bc_nodes(), np.unique(c["bc_nodes"]))
+    assert np.array_equal(M.indptr, c["A_indptr"]) and np.array_equal(M.data, c["A_data"])
+    M2 = adapter.as_matrix(A, V)                                # bare SciPy matrix: Dirichlet nodes = its identity rows
+    assert np.array_equal(M2.bc_nodes(), np.unique(c["bc_nodes"]))
+
+    class PetscLike(object):                                    # the Firedrake way: A.petscmat.getValuesCSR(), A.bcs[i].nodes
+        class _Mat(object):
+            def getValuesCSR(self_inner):
+                return A.indptr, A.indices, A.data
+        petscmat = _Mat()
+        bcs = [type("BC", (), {"nodes": np.asarray(c["bc_nodes"])})()]
+    M3 = adapter.as_matrix(PetscLike(), V)
+    assert np.array_equal(M3.bc_nodes(), np.unique(c["bc_nodes"])) and np.array_equal(M3.indices, c["A_indices"])
+    f = ff.Function(V, np.arange(n, dtype=np.float64))
+    assert np.array_equal(adapter.function_array(f), np.arange(n)) and np.array_equal(adapter.function_array(f.vector()), np.arange(n))
+    adapter.assign_function(f, np.ones(n))
+    assert np.all(f._data == 1.)
+    assert adapter.is_vector_like(f.vector()) and not adapter.is_vector_like(np.ones(n)) and not adapter.is_vector_like(f)
+    for bad in (object(), 3, "space", np.ones(4)):
+        with pytest.raises(TypeError):
+            adapter.as_function_space(bad)
+    for bad in (object(), np.eye(3), "A"):
+        assert not adapter.looks_like_matrix(bad)
+        with pytest.raises(TypeError):
+            adapter.as_matrix(bad, V)
+    with pytest.raises(TypeError):
+        adapter.as_matrix(sp.eye(n + 1).tocsr(), V)             # wrong size for the space
+
+
+def test_fast_poisson_oracle_solver_matches_direct_lu():
+    "oracle/fast_poisson.py (the CPU checker at sizes where a sparse LU does not fit) against SciPy SuperLU"
+    from stat_fem_b200 import fem
+    from oracle.solver import _DirectSolver
+    from oracle.fast_poisson import DSTSolver
+    rng = np.random.default_rng(0)
+    for nodes, dim in ((33, 2), (13, 3)):
+        V, A, b = fem.poisson_problem(nodes, dim)
+        As = A.to_scipy()
+        lu, ds = _DirectSolver(As, A.bc_nodes()), DSTSolver(As, A.bc_nodes(), nodes, dim)
+        for bcs_on in (False, True):
+            r = rng.normal(size=V.dim())
+            x0, x1 = lu.solve(r, bcs_on), ds.solve(r, bcs_on)
+            assert np.max(np.abs(x0 - x1)) <= 1e-12 * np.max(np.abs(x0))
+            assert ds.residual(x1, r, bcs_on) < 1e-13
+
+
+def test_newton_polish_finds_the_stationary_point_of_a_known_function():
+    "estimation.newton_polish only needs logpost_deriv: a quadratic-plus-quartic bowl with a known minimiser"
+    from stat_fem_b200.estimation import newton_polish
+
+    class Bowl(object):
+        x0 = np.array([0.3, -4.1, -1.2])
+        H = np.array([[40., 3., 1.], [3., 900., 20.], [1., 20., 15.]])
+
+        def logpost_deriv(self, th):
+            d = np.asarray(th) - self.x0
+            return self.H @ d + 50. * d ** 3
+    x, info = newton_polish(Bowl(), Bowl.x0 + np.array([1e-4, -2e-5, 3e-4]))
+    assert info["converged"] and np.max(np.abs(x - Bowl.x0)) < 1e-9
+    far = Bowl.x0 + 5.                                            # not near a minimum of a convex bowl? still contracts or is refused
+    x2, info2 = newton_polish(Bowl(), far)
+    assert info2["converged"] or np.array_equal(x2, far)
