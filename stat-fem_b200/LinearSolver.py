@@ -194,9 +194,10 @@ class LinearSolver(object):
         if flag is not None:
             return bool(flag)
         import torch
-        lo, hi = self.ensemble_comm.column_range(self.data.get_n_obs())
+        # the same answer on every rank (the largest share of the columns decides): the posterior-mean path is collective
+        widest = -(-self.data.get_n_obs() // max(self.ensemble_comm.size, 1))
         total = torch.cuda.get_device_properties(self.solver.ctx.tdev).total_memory
-        return 8. * self.solver.n * (hi - lo) <= 0.25 * total
+        return 8. * self.solver.n * widest <= 0.25 * total
 
     def _aga_p(self, Cmat, collective):
         """A^-1 G A^-1 P C for a block C (n_obs x ns, device) of data-space vectors -> (n x ns) on the ensemble root.
