@@ -50,23 +50,79 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lk = lane & 3;
     PCLK(0);
-    // load the lower triangle: 8 independent loads in flight per thread (each row is a coalesced segment)
-    for (int t0 = tid; t0 < NB * NB; t0 += 256 * 8) {
-        double v[8];
+    // load the lower triangle as 16-byte pairs, 8 independent loads in flight per thread (each row is a coalesced segment);
+    // the upper triangle is zero, rows / columns beyond nb are identity
+    const bool vec2 = (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+    const bool dvec = reinterpret_cast<uintptr_t>(Dinv) % 16 == 0;
+    for (int t0 = tid; t0 < NB * NB / 2; t0 += 256 * 8) {
+        double2 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            int t = t0 + u * 256;
-            int r = t >> 7, cidx = t & (NB - 1);
-            v[u] = (r == cidx) ? 1.0 : 0.0;
-            if (r < nb && cidx <= r) v[u] = A[(int64_t)r * lda + cidx];
+            const int t = t0 + u * 256;
+            const int r = t >> 6, c2 = (t & 63) * 2;
+            v[u] = make_double2((r == c2) ? 1.0 : 0.0, (r == c2 + 1) ? 1.0 : 0.0);
+            if (r < nb && c2 <= r) {
+                const double* g = A + (int64_t)r * lda + c2;
+                if (vec2) {
+                    const double2 w = *reinterpret_cast<const double2*>(g);
+                    v[u].x = w.x;
+                    if (c2 + 1 <= r) v[u].y = w.y;
+                } else {
+                    v[u].x = g[0];
+                    if (c2 + 1 <= r) v[u].y = g[1];
+                }
+                if (c2 + 1 > r) v[u].y = 0.0;
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            int t = t0 + u * 256;
-            s[(t >> 7) * PLD + (t & (NB - 1))] = v[u];
+            const int t = t0 + u * 256;
+            *reinterpret_cast<double2*>(s + (t >> 6) * PLD + (t & 63) * 2) = v[u];
         }
     }
     __syncthreads();
+
+    // Work that does not depend on the diagonal block being factorised (warp 0 alone, ~3 us per block step) is given to
+    // the seven other warps during that window: block column pj is final after its block step, so it is written back to
+    // global memory and then overwritten in place by M = L inv(D_pj), the first half of the inverse (phase 2, step A).
+    auto store_L_cols = [&](int pj, int first, int nthr) {      // rows >= SB*pj of block column pj (its lower part)
+        const int rows = NB - SB * pj;
+        for (int t = first; t < rows * (SB / 2); t += nthr) {
+            const int r = SB * pj + (t >> 4), c2 = SB * pj + (t & 15) * 2;
+            if (r < nb && c2 <= r) {
+                const double2 w = *reinterpret_cast<const double2*>(s + r * PLD + c2);
+                double* g = A + (int64_t)r * lda + c2;
+                if (vec2 && c2 + 1 <= r) *reinterpret_cast<double2*>(g) = w;
+                else {
+                    g[0] = w.x;
+                    if (c2 + 1 <= r) g[1] = w.y;
+                }
+            }
+        }
+    };
+    auto step_A_cols = [&](int pj, int wfirst, int nw) {        // M_k,pj = L_k,pj inv(D_pj) for the block rows k > pj
+        int strip = 0;
+        for (int kb = pj + 1; kb < NB / SB; ++kb)
+            for (int ts = 0; ts < 4; ++ts, ++strip) {
+                if (strip % nw != wfirst) continue;
+                double* rowp = s + (SB * kb + 8 * ts + lr) * PLD + SB * pj;
+                double af[8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) af[ks] = rowp[4 * ks + lk];
+                const double* dv = Dv + pj * SB * DLD;
+                double acc[4][2];
+#pragma unroll
+                for (int tn = 0; tn < 4; ++tn) {
+                    acc[tn][0] = acc[tn][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) dmma_8x8x4(acc[tn][0], acc[tn][1], af[ks], dv[(4 * ks + lk) * DLD + 8 * tn + lr]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int tn = 0; tn < 4; ++tn)
+                    *reinterpret_cast<double2*>(rowp + 8 * tn + 2 * lk) = make_double2(acc[tn][0], acc[tn][1]);
+            }
+    };
 
     // ------------------------------------------------------------------ phase 1: Cholesky by 32-wide block steps
     PCLK(1);
@@ -75,39 +131,74 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
         if (jb == 0) PCLK(2);
         double rinvs[SB];
         if (warp == 0) {
-            double a[SB];
-            const double* rowp = s + (c0 + lane) * PLD + c0;
+            // 32x32 diagonal block in four 8-column sub-steps.  Within a sub-step the columns are eliminated in registers
+            // (lane = row; only the 7 + 6 + ... + 1 = 28 cross-lane exchanges inside the sub-block are shuffles); the rest
+            // of the block is then updated through shared memory with DMMA 8x8x4 tiles (at most 6 tiles, 2 MMAs each).
+            // The all-register version spent 496 shuffle + FMA pairs on the same update: 340 cycles per column against
+            // a dependency chain of ~135.
+            double* blk = s + c0 * PLD + c0;
 #pragma unroll
-            for (int k = 0; k < SB; ++k) a[k] = (k <= lane) ? rowp[k] : 0.0;
-#pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(d > 0.0)) {
-                    if (lane == 0 && *info == 0) *info = j0 + c0 + j + 1;
-                    d = 1.0;
-                }
-                // hardware seed (relative error 2^-22) + two Newton steps: ~1 ulp, no range checks on the critical chain
-                double rinv;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(d));
+            for (int sb8 = 0; sb8 < SB / 8; ++sb8) {
+                double a8[8];
+                double* rowp = blk + lane * PLD + 8 * sb8;
                 {
-                    const double hd = 0.5 * d;
-                    rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
-                    rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
+                    const double2 v0 = *reinterpret_cast<const double2*>(rowp), v1 = *reinterpret_cast<const double2*>(rowp + 2);
+                    const double2 v2 = *reinterpret_cast<const double2*>(rowp + 4), v3 = *reinterpret_cast<const double2*>(rowp + 6);
+                    a8[0] = v0.x; a8[1] = v0.y; a8[2] = v1.x; a8[3] = v1.y; a8[4] = v2.x; a8[5] = v2.y; a8[6] = v3.x; a8[7] = v3.y;
                 }
-                rinvs[j] = rinv;
-                double lij = a[j] * rinv;
-                if (lane == j) { lij = d * rinv; rd[c0 + j] = rinv; }
-                a[j] = lij;
 #pragma unroll
-                for (int k = j + 1; k < SB; ++k) {
-                    double lkj = __shfl_sync(0xffffffffu, lij, k);
-                    a[k] = fma(-lij, lkj, a[k]);
+                for (int t = 0; t < 8; ++t) {
+                    const int j = 8 * sb8 + t;
+                    double d = __shfl_sync(0xffffffffu, a8[t], j);
+                    if (!(d > 0.0)) {
+                        if (lane == 0 && *info == 0) *info = j0 + c0 + j + 1;
+                        d = 1.0;
+                    }
+                    // hardware seed (relative error 2^-22) + two Newton steps: ~1 ulp, no range checks on the critical chain
+                    double rinv;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(d));
+                    {
+                        const double hd = 0.5 * d;
+                        rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
+                        rinv = fma(rinv, fma(-hd, rinv * rinv, 0.5), rinv);
+                    }
+                    rinvs[j] = rinv;
+                    double lij = a8[t] * rinv;
+                    if (lane == j) { lij = d * rinv; rd[c0 + j] = rinv; }
+                    if (lane < j) lij = 0.0;                    // above the diagonal
+                    a8[t] = lij;
+#pragma unroll
+                    for (int u = t + 1; u < 8; ++u) {
+                        double lkj = __shfl_sync(0xffffffffu, lij, 8 * sb8 + u);
+                        a8[u] = fma(-lij, lkj, a8[u]);
+                    }
                 }
+                *reinterpret_cast<double2*>(rowp) = make_double2(a8[0], a8[1]);
+                *reinterpret_cast<double2*>(rowp + 2) = make_double2(a8[2], a8[3]);
+                *reinterpret_cast<double2*>(rowp + 4) = make_double2(a8[4], a8[5]);
+                *reinterpret_cast<double2*>(rowp + 6) = make_double2(a8[6], a8[7]);
+                __syncwarp();
+                // rows and columns 8 (sb8 + 1) .. 31 of the block: C_ij -= L_i L_j^T over the 8 columns just finished
+#pragma unroll
+                for (int ti = sb8 + 1; ti < SB / 8; ++ti)
+#pragma unroll
+                    for (int tj = sb8 + 1; tj <= ti; ++tj) {
+                        const double* ap = blk + (8 * ti + lr) * PLD + 8 * sb8 + lk;
+                        const double* bp = blk + (8 * tj + lr) * PLD + 8 * sb8 + lk;
+                        double acc0 = 0.0, acc1 = 0.0;
+                        dmma_8x8x4(acc0, acc1, ap[0], bp[0]);
+                        dmma_8x8x4(acc0, acc1, ap[4], bp[4]);
+                        double2* cp = reinterpret_cast<double2*>(blk + (8 * ti + lr) * PLD + 8 * tj + 2 * lk);
+                        double2 cv = *cp;
+                        cv.x -= acc0; cv.y -= acc1;
+                        *cp = cv;
+                    }
+                __syncwarp();
             }
-            double* roww = s + (c0 + lane) * PLD + c0;
-#pragma unroll
-            for (int k = 0; k < SB; ++k)
-                if (k <= lane) roww[k] = a[k];
+        } else if (jb > 0) {
+            store_L_cols(jb - 1, tid - 32, 224);
+            asm volatile("bar.sync 1, 224;\n" ::: "memory");       // the seven helper warps: all rows stored before any is overwritten
+            step_A_cols(jb - 1, warp - 1, 7);
         }
         __syncthreads();
         if (jb == 0) PCLK(3);
@@ -150,61 +241,44 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
         }
         __syncthreads();
         if (jb == 0) PCLK(4);
-        // (iii) trailing update of the lower triangle, 8x8 tiles
+        // (iii) trailing update of the lower triangle: a warp takes one 8-row strip and up to four 8x8 column tiles of it
+        // at a time (four independent accumulators: the A fragment is loaded once, the MMAs of a k-step overlap)
         const int mt = (NB - c1) / 8;
         int cnt = 0;
         for (int ti = 0; ti < mt; ++ti) {
-            for (int tj = 0; tj <= ti; ++tj, ++cnt) {
+            for (int tj0 = 0; tj0 <= ti; tj0 += 4, ++cnt) {
                 if ((cnt & 7) != warp) continue;
+                const int ntj = min(4, ti + 1 - tj0);
                 const double* ap = s + (c1 + 8 * ti + lr) * PLD + c0 + lk;
-                const double* bp = s + (c1 + 8 * tj + lr) * PLD + c0 + lk;
-                double acc0 = 0.0, acc1 = 0.0;
+                const double* bp = s + (c1 + 8 * tj0 + lr) * PLD + c0 + lk;
+                double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-                for (int ks = 0; ks < SB / 4; ++ks) dmma_8x8x4(acc0, acc1, ap[4 * ks], bp[4 * ks]);
-                double2* cp = reinterpret_cast<double2*>(s + (c1 + 8 * ti + lr) * PLD + c1 + 8 * tj + 2 * lk);
-                double2 cv = *cp;
-                cv.x -= acc0; cv.y -= acc1;
-                *cp = cv;
+                for (int ks = 0; ks < SB / 4; ++ks) {
+                    const double av = ap[4 * ks];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ntj) dmma_8x8x4(acc[q][0], acc[q][1], av, bp[q * 8 * PLD + 4 * ks]);
+                }
+                double2* cp = reinterpret_cast<double2*>(s + (c1 + 8 * ti + lr) * PLD + c1 + 8 * tj0 + 2 * lk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < ntj) {
+                        double2 cv = cp[q * 4];
+                        cv.x -= acc[q][0]; cv.y -= acc[q][1];
+                        cp[q * 4] = cv;
+                    }
             }
         }
         __syncthreads();
         if (jb == 0) PCLK(5);
     }
     PCLK(6);
-#pragma unroll 8
-    for (int t = tid; t < NB * NB; t += 256) {
-        int r = t >> 7, cidx = t & (NB - 1);
-        if (r < nb && cidx <= r) A[(int64_t)r * lda + cidx] = s[r * PLD + cidx];
-    }
-    __syncthreads();
+    store_L_cols(NB / SB - 1, tid, 256);
     PCLK(7);
-
     // ------------------------------------------------------------------ phase 2: inv(L) in place
-    // step A: M_kj = L_kj inv(D_j); each warp owns whole 8-row strips, so the update is safe in place
-    {
-        int strip = 0;
-        for (int kb = 1; kb < 4; ++kb)
-            for (int jb = 0; jb < kb; ++jb)
-                for (int ts = 0; ts < 4; ++ts, ++strip) {
-                    if ((strip & 7) != warp) continue;
-                    double* rowp = s + (SB * kb + 8 * ts + lr) * PLD + SB * jb;
-                    double af[8];
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) af[ks] = rowp[4 * ks + lk];
-                    const double* dv = Dv + jb * SB * DLD;
-                    double acc[4][2];
-#pragma unroll
-                    for (int tn = 0; tn < 4; ++tn) {
-                        acc[tn][0] = acc[tn][1] = 0.0;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) dmma_8x8x4(acc[tn][0], acc[tn][1], af[ks], dv[(4 * ks + lk) * DLD + 8 * tn + lr]);
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int tn = 0; tn < 4; ++tn)
-                        *reinterpret_cast<double2*>(rowp + 8 * tn + 2 * lk) = make_double2(acc[tn][0], acc[tn][1]);
-                }
-    }
+    // step A (M_kj = L_kj inv(D_j)) of the first three block columns was done by the helper warps above; the last block
+    // column has no rows below its diagonal block.  Its diagonal block is read by the store above and overwritten below.
+    __syncthreads();
     // diagonal blocks <- inv(D_j)
     for (int t = tid; t < 4 * SB * SB; t += 256) {
         int jb = t >> 10, r = (t >> 5) & 31, cidx = t & 31;
@@ -236,9 +310,15 @@ __global__ void __launch_bounds__(256, 1) potrf_panel_kernel(double* __restrict_
             }
     }
     PCLK(9);
-    for (int t = tid; t < NB * NB; t += 256) {
-        int r = t >> 7, cidx = t & (NB - 1);
-        Dinv[t] = (r < nb && cidx <= r && cidx < nb) ? s[r * PLD + cidx] : 0.0;
+    for (int t = tid; t < NB * NB / 2; t += 256) {          // Dinv is a 128 x 128 block of its own: always 16-byte aligned
+        const int r = t >> 6, c2 = (t & 63) * 2;
+        double2 w = make_double2(0.0, 0.0);
+        if (r < nb && c2 <= r) {
+            w = *reinterpret_cast<const double2*>(s + r * PLD + c2);
+            if (c2 + 1 > r) w.y = 0.0;
+        }
+        if (dvec) *reinterpret_cast<double2*>(Dinv + 2 * t) = w;
+        else { Dinv[2 * t] = w.x; Dinv[2 * t + 1] = w.y; }
     }
     PCLK(10);
 }
@@ -288,7 +368,12 @@ static void* dense_tmp(sfem_ctx* c, size_t bytes) {
 // traffic).  The panel solve writes to a temporary (so it may use small tiles and fill the machine) and the copy back
 // into A is off the critical path.
 static int potrf_lower_blocked(sfem_ctx* c, int n, double* A, int64_t lda, double* dinv, int* info_dev) {
-    constexpr int NB2 = 512;
+    // column-block width: 512 keeps the big trailing updates at K = 512 (28 TFLOP/s against 25 at K = 256), which is what
+    // matters from ~8000 observations up; below that the factorisation is a latency chain and the narrower block shortens
+    // the in-block updates that sit on it (SFEM_POTRF_NB2 overrides, for A/B timing)
+    static int nb2_env = -1;
+    if (nb2_env < 0) { const char* e = getenv("SFEM_POTRF_NB2"); nb2_env = e ? atoi(e) : 0; }
+    const int NB2 = nb2_env > 0 ? nb2_env : (n <= 6144 ? 256 : 512);
     CUDA_TRY(c, cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
     size_t dyn = sizeof(double) * (NB * PLD + 4 * SB * DLD + NB);
     static bool attr_set = false;

@@ -16,7 +16,7 @@ torch.cuda.synchronize()
 buf = (C.c_longlong * 16)()
 lib.sfem_debug_panel_clocks(buf)
 c = list(buf)
-names = ["load", "-", "(i) diag factor jb=0", "(ii)+trsm jb=0", "(iii) syrk jb=0", "rest of phase 1 (jb=1..3)", "store L", "phase 2A", "phase 2B", "store Dinv"]
+names = ["load", "-", "(i) diag factor jb=0", "(ii)+trsm jb=0", "(iii) syrk jb=0", "rest of phase 1 (jb=1..3)", "store L (last block column)", "diag blocks <- inverse", "phase 2B", "store Dinv"]
 for i in range(10):
     print("%-28s %7d cycles  %6.2f us" % (names[i], c[i + 1] - c[i], (c[i + 1] - c[i]) / 1965.))
 print("total %.2f us" % ((c[10] - c[0]) / 1965.))
