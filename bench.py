@@ -117,6 +117,7 @@ def gpu_step(prob, comm, resident, stats=None):
         solvers = fit_snapshots(ls, ods, start=np.zeros(3), polish=True, accept_precision_floor=True, **MAP_OPTIONS)
         out["map_messages"] = sorted({str(getattr(s_, "minimize_result", {}).get("message", "(fitted on another rank)")) for s_ in solvers})
         out["evals_per_fit"] = [int(s_.n_logpost_evals) for s_ in solvers]
+        out["eval_cache_hits_per_fit"] = [int(s_.n_logpost_cache_hits) for s_ in solvers]
         for lss in solvers:
             out["thetas"].append(lss.params.copy())
             out["evals"] += lss.n_logpost_evals
@@ -367,7 +368,7 @@ def run_gpu(args):
         "phases_tflops": {k: round(v["flops"] / v["ms"] * 1e-9, 2) for k, v in full_prof.items() if v["count"] and v["flops"] > 0 and v["ms"] > 0},
     }
     for k, v in res.items():
-        if k in ("logpost_first", "logpost_last", "cuy_trace", "x_norm", "mu0", "map_messages", "evals_per_fit"):
+        if k in ("logpost_first", "logpost_last", "cuy_trace", "x_norm", "mu0", "map_messages", "evals_per_fit", "eval_cache_hits_per_fit"):
             line["config"][k] = v
     if parity_inputs is not None:
         line["parity"] = _parity_check(prob, parity_inputs)

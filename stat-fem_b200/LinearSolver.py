@@ -4,6 +4,7 @@ Caches the prior solution x, its interpolation mu and the interpolated prior cov
 210-222) -- here on the device as well as on the host -- and evaluates every dense n_obs x n_obs quantity with the
 FP64 tensor-core kernels (csrc/dgemm.cu, chol.cu, dense_ops.cu)."""
 import ctypes as C
+from collections import OrderedDict
 import numpy as np
 from scipy.linalg import LinAlgError
 from . import _lib
@@ -14,6 +15,8 @@ from .ForcingCovariance import ForcingCovariance
 from .InterpolationMatrix import InterpolationMatrix
 from .ObsData import ObsData
 from .solving_utils import SparseSolver, interp_covariance_to_data, _aga_device
+
+_EVAL_CACHE_POINTS = 8       # recent (theta -> value, gradient) pairs kept by LinearSolver._evaluate
 
 
 class LinearSolver(object):
@@ -62,6 +65,7 @@ class LinearSolver(object):
         self._cache = None
         self.fuse_gradient = False      # set by estimate_params_MAP: evaluate value and gradient in one pass
         self.n_logpost_evals = 0
+        self.n_logpost_cache_hits = 0
         self.host_results = True        # False: leave Cu on the device in solve_prior (bench.py's device-resident arm)
 
     def clone_for_data(self, data, private_stream=False):
@@ -84,6 +88,7 @@ class LinearSolver(object):
         other._owns_dense_ctx = bool(private_stream)
         other._data_dev = None
         other.n_logpost_evals = 0
+        other.n_logpost_cache_hits = 0
         other._parent = self          # the clone borrows im / solver / prior: keep their owner (and its __del__) alive
         return other
 
@@ -463,9 +468,16 @@ class LinearSolver(object):
         self.set_params(params)
         if self.Cu is None or self.mu is None:
             self.solve_prior()
+        # A few recent points are remembered, not just the last one: when L-BFGS-B can no longer resolve a decrease
+        # (tolerances below the rounding noise of the objective) its line searches and restarts return to the same
+        # theta again and again; the value is a pure function of (theta, prior, data), so those cost nothing.
         key = self.params.tobytes()
-        if self._cache is not None and self._cache[0] == key and (self._cache[2] is not None or not need_grad):
-            return self._cache[1], self._cache[2]
+        if self._cache is not None:
+            hit = self._cache.get(key)
+            if hit is not None and (hit[1] is not None or not need_grad):
+                self._cache.move_to_end(key)
+                self.n_logpost_cache_hits += 1
+                return hit
         world = comm_world()
         local = bool(self.__dict__.get("_local_eval", False)) and self._Cu_dev is not None
         if world.rank == 0 or local:
@@ -491,7 +503,12 @@ class LinearSolver(object):
             result = world.bcast(result, root=0)
             assert result is not None, "error in broadcasting the log likelihood"
             world.barrier()
-        self._cache = (key, result[0], result[1])
+        if self._cache is None:
+            self._cache = OrderedDict()
+        self._cache[key] = (result[0], result[1])
+        self._cache.move_to_end(key)
+        while len(self._cache) > _EVAL_CACHE_POINTS:
+            self._cache.popitem(last=False)
         return result
 
     def share_prior(self):

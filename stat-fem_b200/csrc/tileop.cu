@@ -188,7 +188,8 @@ __device__ bool td_bins(const unsigned short* __restrict__ ec, const double* __r
     return true;
 }
 
-constexpr int TD_MAXKT = 16;      // k-tiles per row group the builder can form (the kernel keeps DM_KTR of them in registers)
+constexpr int TD_MAXKT = 16;      // k-tiles per row group the builder can form (the kernels keep 8 or 16 of them in registers)
+constexpr int TD_MAXNEED = 128;   // staged rows per chunk of the tensor-core form (64 for the wide-slab kernel)
 
 // k-tiles of one row group from its bins (see above); live[t] bit q: position q of tile t carries a slot of the group
 __device__ int td_form(const TdBins& b, int nneed, unsigned short (*sl)[4], unsigned char* live) {
@@ -226,9 +227,9 @@ __global__ void tile_dmma_count_kernel(int nchunks, int dl, int e8, const int* _
         const int nr = dsc[1], nneed = dsc[2], W = dsc[3];
         const unsigned short* ec = ecol + (size_t)cidx * e8;
         const double* ev = eval + (size_t)cidx * e8;
-        if (nr > 32 || nneed > 64) stats[2] = 1;
+        if (nr > 32 || nneed > TD_MAXNEED) stats[2] = 1;
         const int row0 = g * 8, row1 = min(row0 + 8, nr);
-        if (row0 < row1 && nr <= 32 && nneed <= 64) {
+        if (row0 < row1 && nr <= 32 && nneed <= TD_MAXNEED) {
             TdBins b;
             if (!td_bins(ec, ev, W, row0, row1, b)) stats[2] = 1;
             else {
@@ -279,8 +280,8 @@ __global__ void tile_dmma_fill_kernel(int nchunks, int dl, int e8, int kts, int 
     unsigned short sl[TD_MAXKT][4];
     unsigned char live[TD_MAXKT];
     const int KT = td_form(b, nneed, sl, live);
-    unsigned char where[64];
-    for (int i = 0; i < 64; ++i) where[i] = 0xff;
+    unsigned char where[TD_MAXNEED];
+    for (int i = 0; i < TD_MAXNEED; ++i) where[i] = 0xff;
     for (int t = 0; t < KT; ++t)
         for (int q = 0; q < 4; ++q)
             if (live[t] & (1u << q)) where[sl[t][q]] = (unsigned char)(t * 4 + q);
@@ -587,8 +588,18 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
 // slots with distinct (slot mod 4) by construction -- fall into different 32-byte bank groups without any swizzle.
 // Dot products (TM_MULT_DOT / TM_JACOBI_DOT) are transposed through a per-warp scratch and accumulated per column in
 // shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
-constexpr int DM_PITCH = 544;     // bytes between staged rows (512 + 32)
-constexpr int DM_KTR = 8;         // k-tiles of a row group held in registers
+// Two shapes of the kernel (SLABW = right-hand-side columns per work item):
+//   64: rows pitched 544 bytes, at most 64 staged rows and 8 k-tiles per row group -- 2-D meshes aligned with the lattice;
+//   32: rows pitched 288 bytes, at most 128 staged rows and 16 k-tiles per row group -- 3-D meshes (a 32-row chunk of a
+//       15-point stencil touches ~120 rows) and 2-D meshes that do not align with the lattice.  A warp then owns two
+//       accumulator tiles instead of four, which frees the registers for the longer k-tile list.
+template <int SLABW> struct DmCfg {
+    static constexpr int PITCH = SLABW * 8 + 32;           // bytes between staged rows (pitch = 32 mod 128)
+    static constexpr int KTR = SLABW == 64 ? 8 : 16;       // k-tiles of a row group held in registers
+    static constexpr int MAXNEED = SLABW == 64 ? 64 : 128; // staged rows per chunk
+    static constexpr int NG = SLABW / 16;                  // 8-column accumulator tiles per warp
+    static constexpr int CW = SLABW / 2;                   // columns per warp
+};
 constexpr int DM_NREC = 4;        // chunk-record ring
 constexpr int DM_HDR = 128;       // mbarriers: full[3] at 0, record[4] at 24, empty[3] at 56, chunk-done[4] at 80
 
@@ -634,8 +645,14 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
     return v;
 }
 
-template <int MODE>
+// DREG (dot modes, at most DM_DREG column slabs): the per-column sums are reduced over the 8 rows of a tile with a
+// shuffle reduce-scatter (7 exchanges: afterwards every lane owns ONE of the warp's 32 columns) and accumulated in
+// registers, one per slab; no shared-memory scratch, so the dot modes keep the stage depth of the plain ones.
+constexpr int DM_DREG = 6;
+template <int MODE, bool DREG, int SLABW>
 __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArgs a) {
+    constexpr int DM_PITCH = DmCfg<SLABW>::PITCH, DM_KTR = DmCfg<SLABW>::KTR, NG = DmCfg<SLABW>::NG, CW = DmCfg<SLABW>::CW;
+    constexpr int LROWS = DmCfg<SLABW>::MAXNEED / 8;        // lanes of a warp that issue row copies
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr bool HAS_B = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_RESID || MODE == TM_MULT_ADD);
     constexpr bool HAS_D = (MODE == TM_JACOBI || MODE == TM_JACOBI_DOT || MODE == TM_PRESMOOTH2);
@@ -645,26 +662,29 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     const int lr = lane >> 2, lk = lane & 3;
     const int rg = warp & 3, cpart = warp >> 2;
     const int NST = op.nst;
-    const int nslab = (a.k + 63) >> 6;
+    const int nslab = (a.k + SLABW - 1) / SLABW;
     const int nmine = ((int)op.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int T = nmine * nslab;
-    const unsigned last_bytes = (unsigned)(a.k - (nslab - 1) * 64) * 8u;      // bytes of a row inside the last slab
+    const unsigned last_bytes = (unsigned)(a.k - (nslab - 1) * SLABW) * 8u;   // bytes of a row inside the last slab
     const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
     const unsigned rec_a = sm_a + DM_HDR;
     const unsigned st_a = rec_a + DM_NREC * op.cb_bytes;
     unsigned char* rec0 = sm + DM_HDR;
-    const unsigned colb = (unsigned)(cpart * 32 + lr) * 8u;                     // this lane's B column inside a staged row
-    const unsigned cole = (unsigned)(cpart * 32 + 2 * lk) * 8u;                 // first of its two C columns (tile g: + 64 g)
-    double* scr = reinterpret_cast<double*>(sm + op.off_red) + warp * 256;     // [8 rows][32 columns] transposition scratch
-    double* dacc = reinterpret_cast<double*>(sm + op.off_dacc);                // [8 warps][nslab][32] column sums
+    const unsigned colb = (unsigned)(cpart * CW + lr) * 8u;                     // this lane's B column inside a staged row
+    const unsigned cole = (unsigned)(cpart * CW + 2 * lk) * 8u;                 // first of its two C columns (tile g: + 64 g)
+    double* scr = reinterpret_cast<double*>(sm + op.off_red) + warp * (8 * CW); // [8 rows][CW columns] transposition scratch
+    double* dacc = reinterpret_cast<double*>(sm + op.off_dacc);                // [8 warps][nslab][CW] column sums
 
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(sm_a + 8 * s, 1); mbar_init(sm_a + 56 + 8 * s, 8); }
         for (int b = 0; b < DM_NREC; ++b) { mbar_init(sm_a + 24 + 8 * b, 1); mbar_init(sm_a + 80 + 8 * b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (HAS_DOT)
-        for (int i = tid; i < 8 * nslab * 32; i += 256) dacc[i] = 0.0;
+    if (HAS_DOT && !DREG)
+        for (int i = tid; i < 8 * nslab * CW; i += 256) dacc[i] = 0.0;
+    double dreg[DM_DREG];
+#pragma unroll
+    for (int q = 0; q < DM_DREG; ++q) dreg[q] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
 
@@ -687,7 +707,7 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     auto record = [&](int j) { return reinterpret_cast<const int*>(rec0 + (size_t)(j & 3) * op.cb_bytes); };
     // input rows of item u = (chunk ordinal ju, slab su) into stage `stage`: one bulk copy per row.  cp.async.bulk is a
     // uniform-datapath instruction (the lanes of a warp issue theirs one after the other), so the rows are dealt out
-    // over all eight warps, at most eight lanes each.
+    // over all eight warps, at most LROWS (8 or 16) lanes each.
     const double* urow = nullptr;      // producer side: this lane's input row of the chunk being requested (slab 0 position)
     unsigned udst = 0, unn = 0;
     auto issue_rows = [&](int ju, int su, int stage, unsigned par) {
@@ -696,14 +716,14 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
             wait_record(ju);
             const int* dsc = record(ju);
             unn = (unsigned)dsc[2];
-            const unsigned ss = (unsigned)warp + 8u * (unsigned)lane;      // the builder guarantees at most 64 rows per chunk
-            urow = (lane < 8 && ss < unn) ? a.X + (int64_t)dsc[op.dl + ss] * a.ldx : nullptr;
+            const unsigned ss = (unsigned)warp + 8u * (unsigned)lane;      // the launcher guarantees at most 8 * LROWS rows per chunk
+            urow = (lane < LROWS && ss < unn) ? a.X + (int64_t)dsc[op.dl + ss] * a.ldx : nullptr;
             udst = ss * DM_PITCH;
         }
-        const unsigned rb = (su == nslab - 1) ? last_bytes : 512u;
+        const unsigned rb = (su == nslab - 1) ? last_bytes : (unsigned)SLABW * 8u;
         const unsigned bar = sm_a + 8 * stage;
         if (tid == 0) mbar_expect_tx(bar, unn * rb);
-        if (urow) bulk_g2s(st_a + (unsigned)stage * op.st_bytes + udst, urow + su * 64, rb, bar);
+        if (urow) bulk_g2s(st_a + (unsigned)stage * op.st_bytes + udst, urow + su * SLABW, rb, bar);
     };
 
     for (int j = 0; j < DM_NREC; ++j) request_record(j);
@@ -718,11 +738,11 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
     wait_record(0);
 
     // right-hand side / scaling values of this lane's outputs, fetched one item ahead
-    double bq[4][2], di = 0.0, di2 = 0.0;
+    double bq[NG][2], di = 0.0, di2 = 0.0;
     const double* brow = nullptr;      // this lane's right-hand-side row of the chunk being prefetched
     double* yrow = nullptr;            // its output row of the chunk being computed
 #pragma unroll
-    for (int g = 0; g < 4; ++g) bq[g][0] = bq[g][1] = 0.0;
+    for (int g = 0; g < NG; ++g) bq[g][0] = bq[g][1] = 0.0;
     auto prefetch_b = [&](int r0n, int nrn, int sn) {
         const int r = rg * 8 + lr;
         const bool valid = r < nrn;
@@ -733,11 +753,11 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
         if (HAS_B) {
             const double* Bc = (MODE == TM_MULT_ADD) ? a.Y : a.B;
             const int64_t lds = (MODE == TM_MULT_ADD) ? a.ldy : a.ldb;
-            if (sn == 0) brow = Bc + (int64_t)(r0n + r) * lds + cpart * 32 + 2 * lk;
-            const double* p = brow + sn * 64;
-            const int col0 = sn * 64 + cpart * 32 + 2 * lk;
+            if (sn == 0) brow = Bc + (int64_t)(r0n + r) * lds + cpart * CW + 2 * lk;
+            const double* p = brow + sn * SLABW;
+            const int col0 = sn * SLABW + cpart * CW + 2 * lk;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < NG; ++g) {
                 bq[g][0] = bq[g][1] = 0.0;
                 if (valid && col0 + g * 8 < a.k) { const double2 v = *reinterpret_cast<const double2*>(p + g * 8); bq[g][0] = v.x; bq[g][1] = v.y; }
             }
@@ -784,7 +804,7 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
                     if ((m.z >> lane) & 1u) av[i] = ap[m.w + __popc(m.z & below)];
                 }
             }
-            yrow = a.Y + (int64_t)(r0 + rg * 8 + lr) * a.ldy + cpart * 32 + 2 * lk;
+            yrow = a.Y + (int64_t)(r0 + rg * 8 + lr) * a.ldy + cpart * CW + 2 * lk;
             selfoff = 0xffffffffu;
             if (NEED_SELF && rg * 8 + lr < nr) {
                 const unsigned sl = reinterpret_cast<const unsigned short*>(dsc + 8)[rg * 8 + lr];
@@ -794,33 +814,35 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
         const unsigned stg = st_a + (unsigned)cstage * op.st_bytes;
         mbar_wait(sm_a + 8 * cstage, cpar);
 
-        double acc[4][2];
+        double acc[NG][2];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.0;
-        double bA[4], bB[4];       // B fragments of even / odd k-tiles (static double buffer)
-        {
-            const unsigned ad = stg + so[0];
-            bA[0] = lds_f64<0>(ad); bA[1] = lds_f64<64>(ad); bA[2] = lds_f64<128>(ad); bA[3] = lds_f64<192>(ad);
-        }
+        for (int g = 0; g < NG; ++g) acc[g][0] = acc[g][1] = 0.0;
+        double bA[NG], bB[NG];     // B fragments of even / odd k-tiles (static double buffer)
+        auto load_frag = [&](double (&f)[NG], unsigned ad) {
+            f[0] = lds_f64<0>(ad); f[1] = lds_f64<64>(ad);
+            if (NG == 4) { f[NG - 2] = lds_f64<128>(ad); f[NG - 1] = lds_f64<192>(ad); }
+        };
+        load_frag(bA, stg + so[0]);
 #pragma unroll
         for (int i = 0; i < DM_KTR; ++i) {
             if (i >= nkt) break;
             if (i + 1 < DM_KTR) {       // next k-tile's fragments (an unused tile reads column block 0 of slot 0, harmlessly)
                 const unsigned ad = stg + so[i + 1 < DM_KTR ? i + 1 : i];
-                if (i & 1) { bA[0] = lds_f64<0>(ad); bA[1] = lds_f64<64>(ad); bA[2] = lds_f64<128>(ad); bA[3] = lds_f64<192>(ad); }
-                else { bB[0] = lds_f64<0>(ad); bB[1] = lds_f64<64>(ad); bB[2] = lds_f64<128>(ad); bB[3] = lds_f64<192>(ad); }
+                if (i & 1) load_frag(bA, ad);
+                else load_frag(bB, ad);
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) dmma884(acc[g][0], acc[g][1], av[i], (i & 1) ? bB[g] : bA[g]);
+            for (int g = 0; g < NG; ++g) dmma884(acc[g][0], acc[g][1], av[i], (i & 1) ? bB[g] : bA[g]);
         }
 
         // epilogue: this lane holds row rg*8 + lr, columns cpart*32 + g*8 + 2*lk (+1) of the slab
         const int r = rg * 8 + lr;
         const bool rvalid = r < nr;
-        double* Yr = yrow + slab * 64;
+        double* Yr = yrow + slab * SLABW;
+        double pd[NG][2];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int col = slab * 64 + cpart * 32 + g * 8 + 2 * lk;
+        for (int g = 0; g < NG; ++g) {
+            const int col = slab * SLABW + cpart * CW + g * 8 + 2 * lk;
             double s0 = 0.0, s1 = 0.0;
             if (NEED_SELF && selfoff != 0xffffffffu) {
                 const double2 v = lds_v2f64(stg + selfoff + (unsigned)g * 64u);
@@ -839,14 +861,58 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
             }
             const bool ok = rvalid && col < a.k;
             if (ok) *reinterpret_cast<double2*>(Yr + g * 8) = make_double2(y0, y1);
-            if (HAS_DOT) *reinterpret_cast<double2*>(scr + lr * 32 + g * 8 + 2 * lk) = ok ? make_double2(p0, p1) : make_double2(0.0, 0.0);
+            if (HAS_DOT && DREG) { pd[g][0] = ok ? p0 : 0.0; pd[g][1] = ok ? p1 : 0.0; }
+            if (HAS_DOT && !DREG) *reinterpret_cast<double2*>(scr + lr * CW + g * 8 + 2 * lk) = ok ? make_double2(p0, p1) : make_double2(0.0, 0.0);
         }
-        if (HAS_DOT) {
+        if (HAS_DOT && DREG) {
+            // sum over the 8 rows (lane bits 2..4) of each of this lane's 2 NG columns; every exchange halves the columns
+            // a lane keeps.  NG = 4: bit 4 selects tiles {0,1} / {2,3}, bit 3 the tile of the pair, bit 2 the column of
+            // the pair.  NG = 2: bit 4 the tile, bit 3 the column, and the last exchange is a plain sum (lanes with
+            // bit 2 set hold a duplicate).  Additions commute, so the tree is the same for every column.
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            double r2[2];
+            if (NG == 4) {
+                double q2[2][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        const double keep = b4 ? pd[(i + 2) % NG][par] : pd[i][par], send = b4 ? pd[i][par] : pd[(i + 2) % NG][par];
+                        q2[i][par] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const double keep = b3 ? q2[1][par] : q2[0][par], send = b3 ? q2[0][par] : q2[1][par];
+                    r2[par] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+            } else {
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const double keep = b4 ? pd[1][par] : pd[0][par], send = b4 ? pd[0][par] : pd[1][par];
+                    r2[par] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            double s;
+            if (NG == 4) {
+                const double keep = b2 ? r2[1] : r2[0], send = b2 ? r2[0] : r2[1];
+                s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            } else {
+                const double keep = b3 ? r2[1] : r2[0], send = b3 ? r2[0] : r2[1];
+                const double t = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                s = t + __shfl_xor_sync(0xffffffffu, t, 4);
+            }
+#pragma unroll
+            for (int q = 0; q < DM_DREG; ++q)
+                if (slab == q) dreg[q] += s;
+        }
+        if (HAS_DOT && !DREG) {
             __syncwarp();
             double s = 0.0;
+            if (lane < CW) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) s += scr[q * 32 + lane];
-            dacc[(warp * nslab + slab) * 32 + lane] += s;
+                for (int q = 0; q < 8; ++q) s += scr[q * CW + lane];
+                dacc[(warp * nslab + slab) * CW + lane] += s;
+            }
             __syncwarp();
         }
 
@@ -877,13 +943,25 @@ __global__ void __launch_bounds__(256, 2) tileop_dmma_kernel(TileDev op, TileArg
         if (++cstage == NST) { cstage = 0; cpar ^= 1u; }
     }
     if (HAS_DOT) {
-        __syncthreads();
-        for (int i = tid; i < nslab * 64; i += 256) {
-            const int sl = i >> 6, c = i & 63, cp = c >> 5, cc = c & 31;
+        __syncthreads();      // every item consumed: no bulk copy outstanding, the stage buffers are free
+        if (DREG) {
+            // this lane's column inside the warp's CW: NG = 4: tile 2*b4 + b3, pair lk, element b2;  NG = 2: tile b4, element b3
+            const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1;
+            const int cown = NG == 4 ? (b4 * 2 + b3) * 8 + 2 * lk + b2 : b4 * 8 + 2 * lk + b3;
+            dacc = reinterpret_cast<double*>(sm + DM_HDR + DM_NREC * (size_t)op.cb_bytes);
+            if (NG == 4 || b2 == 0) {
+#pragma unroll
+                for (int q = 0; q < DM_DREG; ++q)
+                    if (q < nslab) dacc[(warp * nslab + q) * CW + cown] = dreg[q];
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < nslab * SLABW; i += 256) {
+            const int sl = i / SLABW, c = i % SLABW, cp = c / CW, cc = c % CW;
             double s = 0.0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) s += dacc[((cp * 4 + g) * nslab + sl) * 32 + cc];
-            const int col = sl * 64 + c;
+            for (int g = 0; g < 4; ++g) s += dacc[((cp * 4 + g) * nslab + sl) * CW + cc];
+            const int col = sl * SLABW + c;
             if (col < a.k) a.partials[(size_t)blockIdx.x * a.k + col] = s;
         }
     }
@@ -946,6 +1024,17 @@ __global__ void __launch_bounds__(256) tileop_direct_kernel(TileDev op, TileArgs
 }
 
 inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+// slab width of the tensor-core kernel for an operator: 64 columns when its chunks fit the wide shape, else 32
+// (force32: ctx->tile_dmma == 2, the A/B and parity-test switch for the narrow shape)
+inline int dmma_slab_width(const TileOp& op, bool force32) {
+    if (force32) return 32;
+    return (op.max_need <= DmCfg<64>::MAXNEED && op.max_kt <= DmCfg<64>::KTR) ? 64 : 32;
+}
+inline size_t dmma_pitch(int slabw) { return slabw == 64 ? DmCfg<64>::PITCH : DmCfg<32>::PITCH; }
+inline bool dmma_dot_in_registers(const TileOp& op, int k, bool force32) {
+    const int sw = dmma_slab_width(op, force32), nslab = (k + sw - 1) / sw;
+    return nslab <= DM_DREG && (size_t)op.max_need * dmma_pitch(sw) >= (size_t)8 * nslab * (sw / 2) * sizeof(double);
+}
 
 // shared-memory geometry for one (operator, mode, slab width); returns the total bytes
 size_t tile_layout(const TileOp& op, int mode, int SW, TileDev* d, bool breg = false) {
@@ -992,31 +1081,37 @@ int launch_kernel(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, i
 }
 
 // shared-memory geometry of tileop_dmma_kernel with `nst` stage buffers for k columns; returns the total bytes
-size_t tile_layout_dmma(const TileOp& op, int mode, int k, int nst, TileDev* d) {
-    bool has_dot = (mode == TM_MULT_DOT || mode == TM_JACOBI_DOT);
+size_t tile_layout_dmma(const TileOp& op, int mode, int k, int nst, bool force32, TileDev* d) {
+    // dot modes with at most DM_DREG slabs accumulate in registers (the final exchange reuses the stage buffers:
+    // 8 x nslab x CW doubles <= 12 KB, less than one stage of any operator with 24 or more staged rows)
+    bool has_dot = (mode == TM_MULT_DOT || mode == TM_JACOBI_DOT) && !dmma_dot_in_registers(op, k, force32);
+    const int sw = dmma_slab_width(op, force32), cw = sw / 2;
     size_t cb = (size_t)op.dl * 4 + (size_t)op.n4 * 4 + (size_t)op.kts * 16 + (size_t)op.ap8 * 8;
-    size_t st = (size_t)op.max_need * DM_PITCH;
+    size_t st = (size_t)op.max_need * dmma_pitch(sw);
     size_t tot = DM_HDR + DM_NREC * cb + (size_t)nst * st;
     size_t o_red = tot;
-    if (has_dot) tot += 8 * 256 * sizeof(double);
+    if (has_dot) tot += 8 * 8 * (size_t)cw * sizeof(double);
     size_t o_dacc = tot;
-    if (has_dot) tot += 8 * (size_t)((k + 63) / 64) * 32 * sizeof(double);
+    if (has_dot) tot += 8 * (size_t)((k + sw - 1) / sw) * cw * sizeof(double);
     if (d) { d->cb_bytes = (unsigned)cb; d->st_bytes = (unsigned)st; d->off_bs = 0; d->off_drow = 0; d->off_red = (unsigned)o_red; d->off_dacc = (unsigned)o_dacc; d->nst = nst; }
     return tot;
 }
 // stage depth with which two CTAs of tileop_dmma_kernel fit on an SM (0: none)
-int dmma_stages(const TileOp& op, int mode, int k) {
+int dmma_stages(const TileOp& op, int mode, int k, bool force32) {
     for (int nst = 3; nst >= 2; --nst)
-        if (2 * (tile_layout_dmma(op, mode, k, nst, nullptr) + SMEM_RESERVED) <= 227 * 1024) return nst;
+        if (2 * (tile_layout_dmma(op, mode, k, nst, force32, nullptr) + SMEM_RESERVED) <= 227 * 1024) return nst;
     return 0;
 }
 
-template <int MODE>
-int launch_dmma(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int nst, int* nparts) {
-    size_t smem = tile_layout_dmma(op, MODE, a.k, nst, &d);
+template <int MODE, int SLABW>
+int launch_dmma_sw(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int nst, int* nparts) {
+    constexpr bool has_dot = (MODE == TM_MULT_DOT || MODE == TM_JACOBI_DOT);
+    size_t smem = tile_layout_dmma(op, MODE, a.k, nst, SLABW == 32, &d);
+    const bool dreg = has_dot && dmma_dot_in_registers(op, a.k, SLABW == 32);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tileop_dmma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        cudaFuncSetAttribute(tileop_dmma_kernel<MODE, false, SLABW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        if (has_dot) cudaFuncSetAttribute(tileop_dmma_kernel<MODE, has_dot, SLABW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         attr_set = true;
     }
     // persistent grid: two CTAs per SM (register-limited; the caller checked the shared memory).  Three CTAs per SM at
@@ -1024,9 +1119,15 @@ int launch_dmma(sfem_ctx* c, const TileOp& op, TileDev d, const TileArgs& a, int
     const int64_t want = 2 * (int64_t)SFEM_NUM_SMS;
     int grid = (int)((int64_t)op.nchunks < want ? (int64_t)op.nchunks : want);
     if (nparts) *nparts = grid;
-    tileop_dmma_kernel<MODE><<<grid, 256, smem, c->stream>>>(d, a);
+    if (dreg) tileop_dmma_kernel<MODE, has_dot, SLABW><<<grid, 256, smem, c->stream>>>(d, a);
+    else tileop_dmma_kernel<MODE, false, SLABW><<<grid, 256, smem, c->stream>>>(d, a);
     KCHECK(c);
     return SFEM_OK;
+}
+template <int MODE>
+int launch_dmma(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs& a, int nst, int* nparts) {
+    if (dmma_slab_width(op, c->tile_dmma == 2) == 64) return launch_dmma_sw<MODE, 64>(c, op, d, a, nst, nparts);
+    return launch_dmma_sw<MODE, 32>(c, op, d, a, nst, nparts);
 }
 
 template <int CW, int VEC, int MODE>
@@ -1044,7 +1145,7 @@ int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs&
                (a.B == nullptr || (a.ldb % 2 == 0 && reinterpret_cast<uintptr_t>(a.B) % 16 == 0));
     // FP64 tensor-core form: wide blocks on operators with 32-row chunks, if two CTAs fit on an SM
     if (d.kts > 0 && c->tile_dmma && a.k > 32 && a.k % 2 == 0 && al2) {
-        const int nst = dmma_stages(op, MODE, a.k);
+        const int nst = dmma_stages(op, MODE, a.k, c->tile_dmma == 2);
         if (nst) return launch_dmma<MODE>(c, op, d, a, nst, nparts);
     }
     if (a.k <= 4 && tile_layout(op, MODE, 4, nullptr) <= SMEM_CAP) return launch_variant<4, 1, MODE>(c, op, d, a, nparts);
@@ -1089,7 +1190,9 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     sfem_dev_free(stats);
     if (e != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "tileop: k-tile count failed: %s", cudaGetErrorString(e));
-    if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DM_KTR || op->max_need > 64) return SFEM_OK;      // the kernel keeps a row group's k-tiles in registers
+    // the kernels keep a row group's k-tiles in registers: 8 (64-column slabs) or 16 (32-column slabs)
+    if (h[2] || h[0] <= 0 || h[1] > 65535 || h[3] > DmCfg<32>::KTR || op->max_need > DmCfg<32>::MAXNEED) return SFEM_OK;
+    op->max_kt = h[3];
     const int kts = h[0], ap8 = h[1] > 0 ? (h[1] + 1) & ~1 : 2;
     size_t nc = (size_t)op->nchunks;
     CUDA_TRY(c, sfem_dev_malloc(&op->ktmeta, sizeof(uint4) * nc * kts));
@@ -1103,7 +1206,7 @@ static int tileop_build_dmma(sfem_ctx* c, TileOp* op) {
         KCHECK(c);
     }
     op->kts = kts; op->ap8 = ap8;
-    if (getenv("SFEM_DEBUG")) fprintf(stderr, "tileop dmma form: %d k-tiles, %d values per chunk (%d rows, need %d)\n", kts, ap8, op->max_rows, op->max_need);
+    if (getenv("SFEM_DEBUG")) fprintf(stderr, "tileop dmma form: %d k-tiles, %d values per chunk (%d rows, need %d, at most %d k-tiles per row group: %d-column slabs)\n", kts, ap8, op->max_rows, op->max_need, op->max_kt, dmma_slab_width(*op, false));
     return SFEM_OK;
 }
 

@@ -41,6 +41,7 @@ struct TileOp {
     // nonzeros of a block are stored (lane order), located through a 32-bit lane mask.  desc[6] = k-tile counts of the
     // four row groups (one byte each).
     int kts = 0;                      // k-tile records per chunk (stride), 0: form not built
+    int max_kt = 0;                   // most k-tiles of any row group (<= 8: 64-column slabs, <= 16: 32-column slabs)
     int ap8 = 0;                      // packed block values per chunk (stride, even)
     uint4* ktmeta = nullptr;          // [nchunks][kts] {slot0 | slot1 << 16, slot2 | slot3 << 16, lane mask, first value}
     double* apack = nullptr;          // [nchunks][ap8]

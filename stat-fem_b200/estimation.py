@@ -83,7 +83,7 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, polish=False, accept_p
     for s in solvers:
         s._local_eval = True          # every rank holds the prior: no per-evaluation broadcast
     errors = [None] * ndata
-    results = np.zeros((ndata, 4))
+    results = np.zeros((ndata, 5))
 
     def work(i, use_stream):
         try:
@@ -95,6 +95,7 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, polish=False, accept_p
                 _minimize_local(solvers[i], start, minimize_kwargs, polish, accept_precision_floor)
             results[i, :3] = solvers[i].params
             results[i, 3] = solvers[i].n_logpost_evals
+            results[i, 4] = solvers[i].n_logpost_cache_hits
         except BaseException as exc:      # re-raised in the caller
             errors[i] = exc
 
@@ -118,6 +119,7 @@ def fit_snapshots(ls, datas, start=None, concurrent=True, polish=False, accept_p
     for i, s in enumerate(solvers):
         s.set_params(results[i, :3])
         s.n_logpost_evals = int(results[i, 3])
+        s.n_logpost_cache_hits = int(results[i, 4])
         s._local_eval = False
     return solvers
 

@@ -26,6 +26,7 @@ for i in range(4):
     first_best = int(np.argmax(vals <= best + 1e-12 * abs(best)))
     first_close = int(np.argmax(vals <= best + 1e-9 * abs(best)))
     print("fit", i, r.message, "nfev", r.nfev, "nit", r.nit, "evals", len(trace), "first within 1e-9 rel of best at", first_close,
-          "within 1e-12 at", first_best, "time %.3f" % dt, "ms/eval %.2f" % (1e3 * dt / len(trace)))
+          "within 1e-12 at", first_best, "time %.3f" % dt, "ms/eval %.2f" % (1e3 * dt / len(trace)),
+          "device evaluations", c.n_logpost_evals, "cache hits", c.n_logpost_cache_hits)
     tail = vals[-25:] - best
     print("   last 25 f - best:", " ".join("%.1e" % x for x in tail))
