@@ -46,6 +46,7 @@ struct sfem_ctx {
         int* cell_start = nullptr;   // ncell+1
         int* cell_nodes = nullptr;   // n, ascending node index inside each cell
         int64_t max_row_nnz = 0;
+        int max_span = 0;            // largest (last - first + 1) kept column of a row (count pass)
         int64_t nnz = 0;
     } gc;
 

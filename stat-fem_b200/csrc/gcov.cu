@@ -25,6 +25,7 @@ namespace {
 constexpr int GC_WARPS = 4;
 constexpr int GC_CAP = 512;          // entries per row sorted in shared memory by the owning warp
 constexpr int GC_LONG_CAP = 12288;   // entries per row sorted by a whole CTA (dynamic shared memory)
+constexpr int GC_BM_MAXBITS = 65536; // widest column span of a row ranked through a per-warp bitmap (8 KB + 4 KB of prefix counts)
 
 struct GcP {
     int64_t n;
@@ -143,16 +144,23 @@ __global__ void __launch_bounds__(GC_WARPS * 32) gcov_count_kernel(GcP p, int64_
     RowCtx r = make_row(p, i);
     int cnt = 0;
     bool anyb = false;
+    int jlo = INT_MAX, jhi = -1;
     for_candidates(p, r, lane, [&](int j, bool act) {
         bool keep = false, bl = false;
         if (act) eval_pair(p, r, j, keep, bl);
+        if (keep) { jlo = min(jlo, j); jhi = max(jhi, j); }
         unsigned m = __ballot_sync(0xffffffffu, keep);
         cnt += __popc(m);
         anyb |= (__ballot_sync(0xffffffffu, bl) != 0u);
     });
+    for (int o = 16; o > 0; o >>= 1) {
+        jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+        jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+    }
     if (lane == 0) {
         row_nnz[i] = cnt;
         atomicMax(max_nnz, cnt);
+        if (cnt > 0) atomicMax(max_nnz + 2, jhi - jlo + 1);      // counters[2]: widest column span of a row
         if (anyb) {
             int pos = atomicAdd(n_border, 1);
             if (pos < border_cap) border_rows[pos] = (int)i;
@@ -181,9 +189,10 @@ __device__ __forceinline__ void warp_bitonic(int* col, double* val, int S, int l
 
 __global__ void __launch_bounds__(GC_WARPS * 32) gcov_fill_kernel(GcP p, const int64_t* __restrict__ indptr,
                                                                  int32_t* __restrict__ indices,
-                                                                 double* __restrict__ vals, int presorted) {
+                                                                 double* __restrict__ vals, int presorted, int bm_words) {
     __shared__ int scol[GC_WARPS][GC_CAP];
     __shared__ double sval[GC_WARPS][GC_CAP];
+    extern __shared__ __align__(16) unsigned char gc_dyn[];      // bm_words > 0: per warp a bitmap of the row's column span + prefix counts
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t i = (int64_t)blockIdx.x * GC_WARPS + warp;
     if (i >= p.n) return;
@@ -193,12 +202,14 @@ __global__ void __launch_bounds__(GC_WARPS * 32) gcov_fill_kernel(GcP p, const i
     bool in_smem = nnz <= GC_CAP && !presorted;
     int filled = 0;
     unsigned lt = (1u << lane) - 1u;
+    int jlo = INT_MAX, jhi = -1;
     for_candidates(p, r, lane, [&](int j, bool act) {
         bool keep = false, bl = false;
         double v = 0.0;
         if (act) v = eval_pair(p, r, j, keep, bl);
         unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
+            jlo = min(jlo, j); jhi = max(jhi, j);
             int pos = filled + __popc(m & lt);
             if (in_smem) {
                 scol[warp][pos] = j;
@@ -210,7 +221,45 @@ __global__ void __launch_bounds__(GC_WARPS * 32) gcov_fill_kernel(GcP p, const i
         }
         filled += __popc(m);
     });
-    if (in_smem) {
+    if (in_smem && bm_words > 0 && nnz > 0) {
+        // Rank by bitmap instead of sorting: one bit per column of the row's span [jlo, jhi] (the count pass measured the
+        // widest span, the host sized the bitmap), a prefix count per 32-bit word, and every entry goes straight to
+        // position  prefix[word] + popc(bits below)  of the row.  O(entries + span / 32) instead of O(entries log^2).
+        for (int o = 16; o > 0; o >>= 1) {
+            jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+            jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+        }
+        const int stride = (bm_words * 6 + 15) & ~15;
+        unsigned* bm = reinterpret_cast<unsigned*>(gc_dyn + (size_t)warp * stride);
+        unsigned short* pre = reinterpret_cast<unsigned short*>(bm + bm_words);
+        const int nw = ((jhi - jlo) >> 5) + 1;
+        for (int w = lane; w < nw; w += 32) bm[w] = 0u;
+        __syncwarp();
+        for (int t = lane; t < nnz; t += 32) {
+            const int o = scol[warp][t] - jlo;
+            atomicOr(&bm[o >> 5], 1u << (o & 31));
+        }
+        __syncwarp();
+        int carry = 0;
+        for (int w0 = 0; w0 < nw; w0 += 32) {
+            const int w = w0 + lane;
+            const int cw = w < nw ? __popc(bm[w]) : 0;
+            int incl = cw;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (w < nw) pre[w] = (unsigned short)(carry + incl - cw);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        for (int t = lane; t < nnz; t += 32) {
+            const int j = scol[warp][t], o = j - jlo;
+            const int pos = (int)pre[o >> 5] + __popc(bm[o >> 5] & ((1u << (o & 31)) - 1u));
+            indices[base + pos] = j;
+            vals[base + pos] = sval[warp][t];
+        }
+    } else if (in_smem) {
         int S = 2;
         while (S < nnz) S <<= 1;
         for (int t = nnz + lane; t < S; t += 32) {
@@ -344,7 +393,7 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
     int64_t* row_nnz = reinterpret_cast<int64_t*>(s);
     int64_t* sums = row_nnz + n;
     int* counters = reinterpret_cast<int*>(sums + nsum);
-    CUDA_TRY(c, cudaMemsetAsync(counters, 0, 2 * sizeof(int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(counters, 0, 3 * sizeof(int), c->stream));
     p = make_params(c);
     {
         ProfScope ps(c, TAG_GCOV_COUNT, 8.0 * (double)n * (d + 2), 0.0);
@@ -354,11 +403,12 @@ int gcov_count(sfem_ctx* c, int64_t n, int d, const double* coords, const double
     }
     rc = exclusive_scan<int64_t>(c, row_nnz, n, indptr_out, sums);
     if (rc) return rc;
-    int hc[2];
+    int hc[3];
     CUDA_TRY(c, cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(nnz_out, indptr_out + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     g.max_row_nnz = hc[0];
+    g.max_span = hc[2];
     g.nnz = *nnz_out;
     if (max_row_nnz_out) *max_row_nnz_out = hc[0];
     if (n_borderline_out) *n_borderline_out = hc[1];
@@ -375,7 +425,13 @@ int gcov_fill(sfem_ctx* c, const int64_t* indptr, int32_t* indices_out, double* 
     {
         // algorithmic bytes: 12 per stored entry + row pointers + coordinates and basis integrals
         ProfScope ps(c, TAG_GCOV_FILL, 12.0 * (double)g.nnz + 8.0 * (double)(g.n + 1) + 8.0 * (double)g.n * (g.d + 1), 0.0);
-        gcov_fill_kernel<<<(unsigned)cdiv64(g.n, GC_WARPS), GC_WARPS * 32, 0, c->stream>>>(p, indptr, indices_out, vals_out, presorted);
+        // rows are ordered by bitmap rank when the widest column span fits a per-warp bitmap of at most 64 Ki bits
+        // (structured and bandwidth-reduced numberings); otherwise by the bitonic sort in shared memory
+        int bm_words = (!presorted && g.max_span > 0 && g.max_span <= GC_BM_MAXBITS && !getenv("SFEM_GCOV_BITONIC")) ? (g.max_span + 31) / 32 : 0;
+        size_t dyn = bm_words ? (size_t)GC_WARPS * (((size_t)bm_words * 6 + 15) & ~(size_t)15) : 0;
+        if (dyn > 48 * 1024 - sizeof(int) * GC_WARPS * GC_CAP - sizeof(double) * GC_WARPS * GC_CAP)
+            cudaFuncSetAttribute(gcov_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        gcov_fill_kernel<<<(unsigned)cdiv64(g.n, GC_WARPS), GC_WARPS * 32, dyn, c->stream>>>(p, indptr, indices_out, vals_out, presorted, bm_words);
         KCHECK(c);
     }
     if (!presorted && g.max_row_nnz > GC_CAP) {

@@ -77,6 +77,7 @@ class SparseSolver(object):
         self.max_it = int(params.get("ksp_max_it", 500 if self.precond else 20000))
         self.block_size = params.get("block_size", None)
         self.workspace_gb = float(params.get("workspace_gb", 24.))
+        self._workspace_gb_given = "workspace_gb" in params
         self.mg_nu = int(params.get("mg_nu", 2))
         # damped Jacobi by default (measured on the Poisson meshes of BASELINE.json: as few CG iterations as degree-2
         # Chebyshev weights); mg_omega2 sets a different weight for every second sweep (polynomial smoothing)
@@ -157,10 +158,37 @@ class SparseSolver(object):
             return max(1, min(int(self.block_size), ncols))
         per_col = self.n * 8 * 7.
         kb = int(self.workspace_gb * 1.e9 / per_col)
+        if kb < 192 and not self._workspace_gb_given:
+            # large meshes: blocks narrower than three 64-column slabs leave the per-chunk costs of the tile kernels
+            # unamortised (4M DOF: 64-column blocks ran at 0.59 of the HBM roofline); take up to 40 % of the memory that
+            # is free right now to reach 192 columns
+            import torch
+            free = torch.cuda.mem_get_info(self.ctx.device)[0]       # plus what torch's allocator holds but does not use
+            free += torch.cuda.memory_reserved(self.ctx.device) - torch.cuda.memory_allocated(self.ctx.device)
+            kb = max(kb, min(int(0.4 * free / per_col), 192))
         kb = max(8, min(kb, 512))
         if kb >= 64:
             kb -= kb % 64
         return max(1, min(kb, ncols))
+
+    @staticmethod
+    def block_ranges(ncols, kb):
+        """(first column, width) of the blocks ``ncols`` columns are solved in, at most ``kb`` wide.  The tile kernels
+        work through a block in slabs of 64 columns and their per-chunk costs are shared by the slabs of a block, so the
+        slabs are dealt out evenly over the fewest blocks (512 columns: 256 + 256 rather than 384 + 128) without
+        adding a slab."""
+        if kb < 64 or ncols <= kb:
+            return [(j0, min(kb, ncols - j0)) for j0 in range(0, ncols, kb)]
+        per = kb // 64
+        slabs = -(-ncols // 64)
+        nb = -(-slabs // per)
+        base, extra = divmod(slabs, nb)
+        out, j0 = [], 0
+        for i in range(nb):
+            k = min(64 * (base + (1 if i < extra else 0)), ncols - j0)
+            out.append((j0, k))
+            j0 += k
+        return out
 
     def _workspace(self, k):
         need = _lib.lib().sfem_solve_workspace_bytes(self.ctx.handle, k, self.precond)
@@ -192,8 +220,7 @@ class SparseSolver(object):
         kb = self.pick_block_size(ncols)
         rhs = ctx.empty((self.n, kb + (kb & 1)))
         self.block_iterations = []
-        for j0 in range(0, ncols, kb):
-            k = min(kb, ncols - j0)
+        for j0, k in self.block_ranges(ncols, kb):
             B = rhs[:, :k]
             ctx.check(_lib.lib().sfem_scatter_columns(ctx.handle, self.n, _lib.ptr(P_csc.indptr), _lib.ptr(P_csc.indices),
                                                       _lib.ptr(P_csc.data), col_begin + j0, k, _lib.ptr(B), int(B.stride(0))))

@@ -197,6 +197,39 @@ def test_gcov_long_rows_sorted(env):
     np.testing.assert_allclose(v, ov, rtol=1e-13, atol=0.)
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_gcov_bitmap_rank_and_bitonic_sort_agree(env, shuffle, monkeypatch):
+    """The fill kernel orders a row's entries by bitmap rank when the widest column span fits its per-warp bitmap
+    (structured numbering) and by the bitonic sort otherwise (here: randomly renumbered nodes, span ~ n); both orders,
+    and the forced bitonic path, give the oracle's CSR."""
+    import stat_fem_b200 as stat_fem
+    from stat_fem_b200 import fem
+    import oracle
+    V0, A, b = fem.poisson_problem(300 if shuffle else 129, 2)
+    coords, cells = V0.mesh().coords, V0.mesh().cells
+    if shuffle:
+        perm = np.random.default_rng(5).permutation(coords.shape[0])
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.size)
+        coords, cells = coords[perm], inv[cells]
+    h = 1. / (np.sqrt(coords.shape[0]) - 1)
+    sig, l = np.log(2.e-2), np.log((1.5 if shuffle else 2.2) * h)
+    reg = 1.e-8 * h ** 4 * np.exp(2 * sig)
+    out = []
+    for force_bitonic in (False, True):
+        if force_bitonic:
+            monkeypatch.setenv("SFEM_GCOV_BITONIC", "1")
+        else:
+            monkeypatch.delenv("SFEM_GCOV_BITONIC", raising=False)
+        G, V = _assemble_G(stat_fem, fem, coords, cells, sig, l, 1.e-3, reg)
+        out.append(G.G.to_host())
+    oip, oix, ov = oracle.compute_G_csr_fast(V.coords, V.integrate_basis_functions(), sig, l, 1.e-3, reg)
+    for ip, ix, v in out:
+        assert np.array_equal(ip, oip) and np.array_equal(ix, oix)
+        np.testing.assert_allclose(v, ov, rtol=1e-13, atol=0.)
+    assert np.array_equal(out[0][2], out[1][2])
+
+
 @pytest.mark.parametrize("dim,nodes,pc", [(1, 11, "mg"), (2, 33, "jacobi"), (2, 33, "mg"), (2, 130, "mg"), (2, 257, "mg"), (3, 18, "mg"), (3, 33, "mg")])
 def test_block_solve_matches_direct(env, dim, nodes, pc):
     "Z = A^-1 P for random sensors against SuperLU, every column to 1e-9 relative"

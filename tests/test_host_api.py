@@ -264,3 +264,17 @@ def test_newton_polish_finds_the_stationary_point_of_a_known_function():
     far = Bowl.x0 + 5.                                            # not near a minimum of a convex bowl? still contracts or is refused
     x2, info2 = newton_polish(Bowl(), far)
     assert info2["converged"] or np.array_equal(x2, far)
+
+
+def test_block_ranges_deal_slabs_evenly():
+    "SparseSolver.block_ranges: contiguous cover, no block wider than the limit, never more 64-column slabs than the plain split"
+    from stat_fem_b200.solving_utils import SparseSolver
+    for ncols, kb in [(512, 384), (4096, 384), (2048, 384), (1024, 192), (500, 384), (385, 384), (100, 384), (70, 32), (8, 8), (449, 384)]:
+        r = SparseSolver.block_ranges(ncols, kb)
+        assert r[0][0] == 0 and sum(k for _, k in r) == ncols
+        assert all(0 < k <= kb for _, k in r)
+        assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+        plain = [(j0, min(kb, ncols - j0)) for j0 in range(0, ncols, kb)]
+        assert len(r) == len(plain)
+        assert sum(-(-k // 64) for _, k in r) <= sum(-(-k // 64) for _, k in plain)
+    assert [k for _, k in SparseSolver.block_ranges(512, 384)] == [256, 256]
