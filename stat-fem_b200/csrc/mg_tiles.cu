@@ -417,12 +417,21 @@ int mg_build_tiles(sfem_ctx* c) {
                                                                                c->mg_omega2 / c->mg_omega, L->dinv_t2);
         c->launches++;
     }
-    // restrictions gather ~5 input rows per output row: their chunks are the level's chunks split into pieces of 8
-    // rows, which keeps the staged working set (and with it the number of resident CTAs) like that of the other operators
+    // restrictions gather ~5 input rows per output row.  On the level's own 32-row chunks a 2-D restriction stages 153
+    // rows: that fits the 32-column-slab shape of the tensor-core kernel, which is tried first.  Where it does not apply
+    // (3-D: 405 rows per chunk; tensor-core form switched off) the chunks are split into pieces of 8 rows for the scalar
+    // kernel, which keeps the staged working set (and with it the number of resident CTAs) like that of the other operators
     auto build_restriction = [&](auto gen, int l_rows, int64_t nrows, int64_t ncols, TileOp* out) -> int {
         const int sub = 8;
         int parts = (max_rows[l_rows] + sub - 1) / sub;
         if (parts <= 1) return build_op(c, gen, nrows, ncols, chunk_ptr[l_rows], nchunks[l_rows], max_rows[l_rows], out);
+        if (c->tile_dmma && max_rows[l_rows] > 16 && max_rows[l_rows] <= 32 && !getenv("SFEM_RESTRICT_SCALAR")) {
+            int r = build_op(c, gen, nrows, ncols, chunk_ptr[l_rows], nchunks[l_rows], max_rows[l_rows], out);
+            if (r == SFEM_OK && tileop_dmma_usable(*out)) return SFEM_OK;
+            tileop_free(out);
+            if (r != SFEM_OK && r != SFEM_ERR_LIMIT) return r;
+            if (r == SFEM_ERR_LIMIT) c->err[0] = 0;
+        }
         int* fine = nullptr;
         int nf = nchunks[l_rows] * parts;
         if (sfem_dev_malloc(&fine, sizeof(int) * ((size_t)nf + 1)) != cudaSuccess) return sfem_fail(c, SFEM_ERR_CUDA, "mg tiles: out of memory");

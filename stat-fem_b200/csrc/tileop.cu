@@ -189,7 +189,7 @@ __device__ bool td_bins(const unsigned short* __restrict__ ec, const double* __r
 }
 
 constexpr int TD_MAXKT = 16;      // k-tiles per row group the builder can form (the kernels keep 8 or 16 of them in registers)
-constexpr int TD_MAXNEED = 128;   // staged rows per chunk of the tensor-core form (64 for the wide-slab kernel)
+constexpr int TD_MAXNEED = 160;   // staged rows per chunk of the tensor-core form (64 for the wide-slab kernel)
 
 // k-tiles of one row group from its bins (see above); live[t] bit q: position q of tile t carries a slot of the group
 __device__ int td_form(const TdBins& b, int nneed, unsigned short (*sl)[4], unsigned char* live) {
@@ -590,13 +590,14 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
 // shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
 // Two shapes of the kernel (SLABW = right-hand-side columns per work item):
 //   64: rows pitched 544 bytes, at most 64 staged rows and 8 k-tiles per row group -- 2-D meshes aligned with the lattice;
-//   32: rows pitched 288 bytes, at most 128 staged rows and 16 k-tiles per row group -- 3-D meshes (a 32-row chunk of a
-//       15-point stencil touches ~120 rows) and 2-D meshes that do not align with the lattice.  A warp then owns two
+//   32: rows pitched 288 bytes, at most 160 staged rows and 16 k-tiles per row group -- 3-D meshes (a 32-row chunk of a
+//       15-point stencil touches ~120 rows), 2-D meshes that do not align with the lattice, and the 2-D restrictions
+//       (an 8x4 tile of coarse nodes gathers 17x9 = 153 fine rows).  A warp then owns two
 //       accumulator tiles instead of four, which frees the registers for the longer k-tile list.
 template <int SLABW> struct DmCfg {
     static constexpr int PITCH = SLABW * 8 + 32;           // bytes between staged rows (pitch = 32 mod 128)
     static constexpr int KTR = SLABW == 64 ? 8 : 16;       // k-tiles of a row group held in registers
-    static constexpr int MAXNEED = SLABW == 64 ? 64 : 128; // staged rows per chunk
+    static constexpr int MAXNEED = SLABW == 64 ? 64 : 160; // staged rows per chunk (a multiple of 8: MAXNEED / 8 lanes of every warp issue row copies)
     static constexpr int NG = SLABW / 16;                  // 8-column accumulator tiles per warp
     static constexpr int CW = SLABW / 2;                   // columns per warp
 };
@@ -1162,6 +1163,8 @@ int launch_mode(sfem_ctx* c, const TileOp& op, const TileDev& d, const TileArgs&
 }
 
 }  // namespace
+
+bool tileop_dmma_usable(const TileOp& op) { return op.kts > 0 && dmma_stages(op, TM_MULT, 64, false) > 0; }
 
 void tileop_free(TileOp* op) {
     if (!op) return;

@@ -76,5 +76,7 @@ int tileop_build(sfem_ctx* c, int64_t nrows, int64_t ncols, const int64_t* ptr, 
 // eval_scaled[e] = eval[e] * dinv[column of e]   (dinv in the operator's own numbering; square operators)
 int tileop_scale_columns(sfem_ctx* c, TileOp* op, const double* dinv);
 void tileop_free(TileOp* op);
+// the operator has the tensor-core form and its chunk working set fits two CTAs per SM
+bool tileop_dmma_usable(const TileOp& op);
 // tag: profile family; bytes: algorithmic traffic charged to it; nparts (nullable): rows of a.partials written
 int tileop_apply(sfem_ctx* c, int tag, const TileOp& op, int mode, const TileArgs& a, double bytes, int* nparts = nullptr);

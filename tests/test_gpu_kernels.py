@@ -313,14 +313,16 @@ def test_tile_tensor_form_matches_scalar_form(env, nodes, dim, k):
     gen = torch.Generator(device="cuda").manual_seed(nodes + k)
     checked = 0
     fine_has_form = False
+    restriction_has_form = False
     for level in range(len(ls.mg_levels)):
-        for which, modes in ((0, ("mult_dot", "jacobi", "jacobi_dot", "resid", "presmooth2", "mult")), (1, ("mult_add",))):
+        for which, modes in ((0, ("mult_dot", "jacobi", "jacobi_dot", "resid", "presmooth2", "mult")), (1, ("mult_add",)), (2, ("mult",))):
             rows, cols, form = C.c_int64(0), C.c_int64(0), C.c_int(0)
             ctx.check(lib.sfem_tile_apply_one(ctx.handle, level, which, 0, 0, None, None, None, None, None, 0, C.byref(rows),
                                               C.byref(cols), C.byref(form)))
             if form.value == 0 or rows.value == 0:
                 continue
             fine_has_form |= (level == 0 and which == 0)
+            restriction_has_form |= (level == 0 and which == 2)
             X = torch.rand((cols.value, k), generator=gen, dtype=torch.float64, device="cuda") - 0.5
             B = torch.rand((rows.value, k), generator=gen, dtype=torch.float64, device="cuda") - 0.5
             for name in modes:
@@ -341,6 +343,8 @@ def test_tile_tensor_form_matches_scalar_form(env, nodes, dim, k):
                         assert relerr(d1, d0) < 1e-12, (level, which, name, relerr(d1, d0))
                 checked += 1
     assert fine_has_form, "the stiffness operator has no tensor-core form on this mesh"
+    if dim == 2 and nodes in (65, 129):
+        assert restriction_has_form, "the 2-D restriction (153 staged rows per 32-row chunk) has no tensor-core form"
     assert checked >= 6
 
 
