@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(BREG ? 256 : 512, BREG ? 3 : 1) tileop_kernel(
 // arrived on its "empty" mbarrier, so the loop has no block-wide barrier.  Records travel the same way through a ring
 // of four buffers.  Rows are pitched 544 bytes apart, so the four rows of a B fragment --
 // slots with distinct (slot mod 4) by construction -- fall into different 32-byte bank groups without any swizzle.
-// Dot products (TM_MULT_DOT / TM_JACOBI_DOT) are transposed through a per-warp scratch and accumulated per column in
+// Dot products (TM_MULT_DOT / TM_JACOBI_DOT): reduced over the rows of a tile with warp shuffles into one register per
+// column slab (DREG, at most DM_DREG slabs), else transposed through a per-warp scratch and accumulated per column in
 // shared memory; one row of partials per CTA is written at the end, as in the scalar kernel.
 // Two shapes of the kernel (SLABW = right-hand-side columns per work item):
 //   64: rows pitched 544 bytes, at most 64 staged rows and 8 k-tiles per row group -- 2-D meshes aligned with the lattice;

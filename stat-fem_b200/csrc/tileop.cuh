@@ -14,7 +14,9 @@
 // ever on the critical path.  Each input row is read from L2/HBM about once per kernel instead of once per matrix
 // entry, and the epilogue fuses the vector work of the caller (Jacobi update, residual, dot products).
 //
-// Wide blocks (more than 32 right-hand sides) on operators with 32-row chunks run tileop_dmma_kernel instead: the chunk
+// Wide blocks (more than 32 right-hand sides) on operators with 32-row chunks (at most 160 staged rows and 16 k-tiles
+// per row group: stiffness matrices in 2-D and 3-D, 2-D lattice operators, prolongations, 2-D restrictions) run
+// tileop_dmma_kernel instead, in one of two shapes (64- or 32-column slabs, see DmCfg in tileop.cu): the chunk
 // matrix is applied with FP64 tensor-core instructions (DMMA m8n8k4) from k-tiles of 4 staged slots x 8 rows, the rows
 // are staged by the TMA engine (cp.async.bulk on mbarriers), work items run chunk-major with the block entries held in
 // registers, and the warps are decoupled through full/empty mbarriers (see the comment above that kernel in tileop.cu).
