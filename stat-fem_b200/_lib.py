@@ -295,7 +295,12 @@ def new_stream_context(device=None):
     (``torch.cuda.stream(ctx.tstream)``) so that torch allocations and copies are ordered with the library's kernels."""
     torch = torch_mod()
     dev = torch.cuda.current_device() if device is None else int(device)
-    return Context(dev, stream=torch.cuda.Stream(device=dev))
+    # The private stream gets a high priority, so that the latency chain of a factorisation (panel kernel, panel solve,
+    # in-block update) is scheduled ahead of the bulk trailing updates that the fits queue on their default-priority
+    # side streams: 8 concurrent fits at 4096 sensors 1.72 -> 1.65 s on the same box with identical evaluation counts
+    # (gpurun_out/r2b_t10_prio*.err; SFEM_FIT_PRIORITY=0 switches it off)
+    prio = -1 if os.environ.get("SFEM_FIT_PRIORITY", "1") == "1" else 0
+    return Context(dev, stream=torch.cuda.Stream(device=dev, priority=prio))
 
 
 def destroy_context(ctx):
